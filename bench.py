@@ -1,0 +1,498 @@
+#!/usr/bin/env python
+"""bench.py -- Gaussians/s fwd+bwd of the rasterizer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|cpu] [--workload c1|c2|c3|c5]
+
+A "step" = forward + backward of every view of the workload over one synthetic Gaussian cloud:
+default workload c3 = BASELINE.json configs[2]: 500k Gaussians, 4 views 256x256, RGB + 32 feature channels.
+One JSON line is printed by rank 0.  Keys are described in DESIGN.md ("Measurement").
+
+  value      whole-job Gaussians/s (P * views / s), inputs resident in HBM, through the C ABI (raw calls)
+  e2e        same metric through the public nn.Module/autograd API with pinned-host inputs copied H2D every step
+             and a scalar read back D2H
+  roofline   dominant kernel (backward blend): algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline  the CPU oracle (oracle/gs_oracle.c, OpenMP) timed on a bounded sample of the same workload
+
+--impl reference times the UNMODIFIED reference rasterizer compiled for sm_100 (oracle/_ref, built by
+oracle/build_ref.py) with the identical harness; the reference has no CPU implementation of this path, so the
+CPU leg of both arms is the oracle port.  Under torchrun (N > 1) views are sharded across ranks (weak scaling:
+`views` per GPU) and the packed per-Gaussian gradient buffer is summed with one NCCL all-reduce per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c1": dict(P=50_000, views=1, W=128, H=128, F=0, depth=False, desc="50k Gaussians, 1 view 128x128, RGB-only"),
+    "c2": dict(P=200_000, views=1, W=256, H=256, F=0, depth=True, desc="200k Gaussians, 1 view 256x256, RGB+depth"),
+    "c3": dict(P=500_000, views=4, W=256, H=256, F=32, depth=False, desc="500k Gaussians, 4 views 256x256, RGB+32 feat"),
+    "c5": dict(P=1_000_000, views=1, W=256, H=256, F=32, depth=False, desc="1M Gaussians, 1 view/GPU 256x256, RGB+32 feat"),
+    "mg": dict(P=16_384, views=1, W=128, H=128, F=3, depth=False, desc="ManiGaussian's real call: 16384 Gaussians, 128x128, F=3"),
+}
+SH_DEGREE = 1
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def host_inputs(wl, rank, world):
+    from manigaussian_b200 import scenes
+    P, V, W, H, F = wl["P"], wl["views"], wl["W"], wl["H"], wl["F"]
+    g = scenes.make_gaussians(P, F=F, sh_degree=SH_DEGREE, seed=1234)
+    cams = [scenes.make_camera(W, H, rank * V + v, world * V) for v in range(V)]
+    cts = [scenes.make_cotangents(W, H, F, seed=100 + rank * V + v, depth=wl["depth"]) for v in range(V)]
+    return g, cams, cts
+
+
+class Impl:
+    """fwd(view tensors) -> handle ; bwd(handle, cotangents) -> 9-tuple of gradients (reference order)."""
+    name = "ours"
+
+    def __init__(self, F, depth):
+        from manigaussian_b200 import rasterizer as R
+        self.R, self.F, self.depth = R, F, depth
+
+    def fwd(self, G, cam):
+        out = self.R.rasterize_gaussians_raw(cam["bg"], G["means3D"], G["empty"], G["feature"], G["opacities"], G["scales"],
+                                             G["rotations"], 1.0, G["empty"], cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"],
+                                             cam["tanfovy"], cam["H"], cam["W"], G["shs"], SH_DEGREE, cam["campos"], False, False,
+                                             self.F > 0, return_depth=self.depth)
+        return out
+
+    def bwd(self, G, cam, out, ct):
+        return self.R.rasterize_gaussians_backward_raw(
+            cam["bg"], G["means3D"], out[3], G["empty"], G["feature"], G["scales"], G["rotations"], 1.0, G["empty"],
+            cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], ct["dL_dcolor"], ct["dL_dfeature"], G["shs"],
+            SH_DEGREE, cam["campos"], out[4], out[0], out[5], out[6], False, self.F > 0,
+            dL_dout_depth=ct["dL_ddepth"] if self.depth else None)
+
+
+class RefImpl(Impl):
+    """The unmodified reference kernels (oracle/_ref).  The build's feature width is fixed (3 or 32): features are
+    padded to it; depth (absent in the reference) rides in a spare feature channel as SURVEY.md 8(d) prescribes."""
+    name = "reference"
+
+    def __init__(self, F, depth):
+        import torch
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import util
+        self.torch = torch
+        self.F, self.depth = F, depth
+        need = F + (1 if depth else 0)
+        self.Fb = 32 if need > 3 else 3
+        self.mod = util.load_reference(self.Fb)
+        if self.mod is None:
+            raise RuntimeError("oracle/_ref is not built")
+
+    def _feat(self, G, cam):
+        key = ("featb", id(cam))
+        if key not in G:
+            t = self.torch.zeros((G["means3D"].shape[0], self.Fb), device="cuda")
+            if self.F:
+                t[:, :self.F] = G["feature"]
+            if self.depth:
+                vm = cam["viewmatrix"].reshape(-1)
+                t[:, self.F] = G["means3D"] @ self.torch.stack([vm[2], vm[6], vm[10]]) + vm[14]
+            G[key] = t
+        return G[key]
+
+    def fwd(self, G, cam):
+        inc = (self.F > 0) or self.depth
+        return self.mod.rasterize_gaussians(cam["bg"], G["means3D"], G["empty"], self._feat(G, cam), G["opacities"], G["scales"],
+                                            G["rotations"], 1.0, G["empty"], cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"],
+                                            cam["tanfovy"], cam["H"], cam["W"], G["shs"], SH_DEGREE, cam["campos"], False, False, inc)
+
+    def bwd(self, G, cam, out, ct):
+        inc = (self.F > 0) or self.depth
+        key = ("ctb", id(ct))
+        if key not in G:
+            t = self.torch.zeros((self.Fb, cam["H"], cam["W"]), device="cuda")
+            if self.F:
+                t[:self.F] = ct["dL_dfeature"]
+            if self.depth:
+                t[self.F] = ct["dL_ddepth"]
+            G[key] = t
+        return self.mod.rasterize_gaussians_backward(
+            cam["bg"], G["means3D"], out[3], G["empty"], self._feat(G, cam), G["scales"], G["rotations"], 1.0, G["empty"],
+            cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], ct["dL_dcolor"], G[key], G["shs"], SH_DEGREE,
+            cam["campos"], out[4], out[0], out[5], out[6], False, inc)
+
+
+def to_device(g, cams, cts, torch, pinned=False):
+    def t(x):
+        if x is None:
+            return None
+        x = torch.from_numpy(np.ascontiguousarray(x))
+        return x.pin_memory() if pinned else x.cuda()
+    G = {k: t(g[k]) for k in ("means3D", "scales", "rotations", "opacities", "shs", "feature")}
+    G["empty"] = torch.Tensor([])
+    C = []
+    for c in cams:
+        d = {k: t(c[k]) for k in ("viewmatrix", "projmatrix", "campos")}
+        d.update(W=c["W"], H=c["H"], tanfovx=c["tanfovx"], tanfovy=c["tanfovy"], bg=t(np.zeros(3, np.float32)))
+        C.append(d)
+    T = [{k: t(v) for k, v in ct.items()} for ct in cts]
+    return G, C, T
+
+
+GRAD_ORDER = ("dL_dmeans2D", "dL_dcolors", "dL_dfeature", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales",
+              "dL_drotations")
+PACKED = ("dL_dmeans3D", "dL_dmeans2D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dsh", "dL_dfeature")
+
+
+def make_packed(P, F, M, torch):
+    """One flat fp32 buffer holding every per-Gaussian gradient the optimiser needs; the all-reduce message."""
+    widths = dict(dL_dmeans3D=3, dL_dmeans2D=3, dL_dscales=3, dL_drotations=4, dL_dopacity=1, dL_dsh=3 * M, dL_dfeature=F)
+    flat = torch.zeros(P * sum(widths.values()), device="cuda")
+    views, off = {}, 0
+    for k in PACKED:
+        n = P * widths[k]
+        if n:
+            views[k] = flat[off:off + n].view(P, widths[k])
+        off += n
+    return flat, views
+
+
+def run_step(impl, G, C, T, flat, acc, dist=None):
+    flat.zero_()
+    Rs = 0
+    for cam, ct in zip(C, T):
+        out = impl.fwd(G, cam)
+        grads = impl.bwd(G, cam, out, ct)
+        Rs += int(out[0])
+        gd = dict(zip(GRAD_ORDER, grads))
+        for k, v in acc.items():
+            v.add_(gd[k].reshape(v.shape))
+    if dist is not None:
+        dist.all_reduce(flat)
+    return Rs
+
+
+# ------------------------------------------------------------------------------------------------ e2e (public API)
+def make_e2e(impl_name, wl, torch):
+    P, F = wl["P"], wl["F"]
+    if impl_name == "ours":
+        from manigaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer
+
+        def render(st, **kw):
+            return GaussianRasterizer(st, return_depth=wl["depth"])(**kw)
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import util
+        from manigaussian_b200 import GaussianRasterizationSettings
+        need = F + (1 if wl["depth"] else 0)
+        Fb = 32 if need > 3 else 3
+        mod = util.load_reference(Fb)
+
+        class _Fn(torch.autograd.Function):  # mirrors DGR/diff_gaussian_rasterization/__init__.py:46-164 around the reference's _C
+            @staticmethod
+            def forward(ctx, means3D, means2D, sh, feat, opac, scales, rots, st):
+                e = torch.Tensor([])
+                n, color, lf, radii, gb, bb, ib = mod.rasterize_gaussians(st.bg, means3D, e, feat, opac, scales, rots, 1.0, e,
+                                                                          st.viewmatrix, st.projmatrix, st.tanfovx, st.tanfovy,
+                                                                          st.image_height, st.image_width, sh, st.sh_degree,
+                                                                          st.campos, False, False, True)
+                ctx.st, ctx.n = st, n
+                ctx.save_for_backward(feat, means3D, scales, rots, radii, sh, gb, bb, ib)
+                return color, lf, radii
+
+            @staticmethod
+            def backward(ctx, gc, gf, _):
+                st = ctx.st
+                feat, means3D, scales, rots, radii, sh, gb, bb, ib = ctx.saved_tensors
+                e = torch.Tensor([])
+                g = mod.rasterize_gaussians_backward(st.bg, means3D, radii, e, feat, scales, rots, 1.0, e, st.viewmatrix,
+                                                     st.projmatrix, st.tanfovx, st.tanfovy, gc.contiguous(), gf.contiguous(), sh,
+                                                     st.sh_degree, st.campos, gb, ctx.n, bb, ib, False, True)
+                return g[4], g[0], g[6], g[2], g[3], g[7], g[8], None
+
+        def render(st, means3D, means2D, opacities, shs, language_feature_precomp, scales, rotations):
+            feat = torch.zeros((P, Fb), device="cuda")
+            k = 0
+            if F:
+                feat = torch.cat([language_feature_precomp, feat[:, F:]], 1)
+                k = F
+            if wl["depth"]:
+                vm = st.viewmatrix.reshape(-1)
+                z = means3D @ torch.stack([vm[2], vm[6], vm[10]]) + vm[14]
+                feat = torch.cat([feat[:, :k], z[:, None], feat[:, k + 1:]], 1)
+            color, lf, radii = _Fn.apply(means3D, means2D, shs, feat, opacities, scales, rotations, st)
+            if wl["depth"]:
+                return color, lf[:F], radii, lf[F]
+            return color, lf[:F], radii
+
+    def step(Gh, Ch, Th):
+        """One end-to-end step from pinned host memory: H2D of the step's inputs, render + loss + backward, D2H of the loss."""
+        G = {k: (v.cuda(non_blocking=True).requires_grad_(True) if v is not None and v.numel() else v) for k, v in Gh.items()}
+        loss = 0.0
+        for ch, th in zip(Ch, Th):
+            cam = {k: (v.cuda(non_blocking=True) if hasattr(v, "cuda") else v) for k, v in ch.items()}
+            ct = {k: (v.cuda(non_blocking=True) if v is not None else None) for k, v in th.items()}
+            st = GaussianRasterizationSettings(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], cam["bg"], 1.0, cam["viewmatrix"],
+                                               cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, F > 0 or impl_name != "ours")
+            kw = dict(means3D=G["means3D"], means2D=torch.zeros_like(G["means3D"], requires_grad=True), opacities=G["opacities"],
+                      shs=G["shs"], language_feature_precomp=G["feature"] if F else None, scales=G["scales"], rotations=G["rotations"])
+            out = render(st, **kw)
+            loss = loss + (out[0] * ct["dL_dcolor"]).sum()
+            if F:
+                loss = loss + (out[1] * ct["dL_dfeature"]).sum()
+            if wl["depth"]:
+                loss = loss + (out[3] * ct["dL_ddepth"]).sum()
+        loss.backward()
+        return float(loss.item())
+
+    return step
+
+
+def nbytes(d):
+    return sum(v.numel() * v.element_size() for v in d.values() if hasattr(v, "numel"))
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(wl, budget_gaussians=100_000):
+    """Oracle port (oracle/gs_oracle.c, all host threads) on a bounded sample of the workload: the first
+    `budget_gaussians` Gaussians of the cloud (same per-Gaussian footprint), view 0, fwd+bwd."""
+    from manigaussian_b200 import scenes
+    from oracle import gs_oracle as O
+    P, W, H, F = wl["P"], wl["W"], wl["H"], wl["F"]
+    Ps = min(P, budget_gaussians)
+    g = scenes.make_gaussians(P, F=F, sh_degree=SH_DEGREE, seed=1234)
+    g = {k: (v[:Ps] if isinstance(v, np.ndarray) else v) for k, v in g.items()}
+    cam = scenes.make_camera(W, H, 0, wl["views"])
+    ct = scenes.make_cotangents(W, H, F, seed=100)
+    bg = np.zeros(3, np.float32)
+    kw = dict(scales=g["scales"], rotations=g["rotations"], shs=g["shs"], sh_degree=SH_DEGREE, feature=g["feature"])
+    cores = O.max_threads()
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        fw = O.forward(g["means3D"], g["opacities"], cam["viewmatrix"], cam["projmatrix"], cam["campos"], W, H, cam["tanfovx"],
+                       cam["tanfovy"], bg, **kw)
+        O.backward(fw, ct["dL_dcolor"], ct["dL_dfeature"], g["means3D"], cam["viewmatrix"], cam["projmatrix"], cam["campos"],
+                   cam["tanfovx"], cam["tanfovy"], bg, **kw)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": Ps / best, "unit": "Gaussians/s", "cores": cores, "kind": "port",
+            "sample": f"first {Ps} of {P} Gaussians, view 0 of {wl['views']}, {W}x{H}, F={F}, fwd+bwd, best of 2 ({best:.2f} s)"}, best
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    wl = dict(WORKLOADS[a.workload])
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    base = {"metric": "Gaussians/s fwd+bwd", "unit": "Gaussians/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": a.impl}
+    cfg = {"workload": f"{a.workload}: {wl['desc']}", "P": wl["P"], "views_per_gpu": wl["views"], "image": [wl["W"], wl["H"]],
+           "feature_channels": wl["F"], "depth": wl["depth"], "sh_degree": SH_DEGREE,
+           "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of packed per-Gaussian grads per step" if world > 1 else "1 GPU"}
+
+    # ---- CPU-only arm / reference arm without a reference build -------------------------------------------------
+    import torch
+    use_cpu = a.impl == "cpu"
+    if a.impl == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import util
+        need = wl["F"] + (1 if wl["depth"] else 0)
+        if not torch.cuda.is_available() or util.load_reference(32 if need > 3 else 3) is None:
+            use_cpu = True
+    if use_cpu:
+        if rank != 0:
+            return 0
+        cb, best = cpu_baseline(wl)
+        out = dict(base, value=cb["value"], ms_per_step=best * 1e3, config=cfg, cpu_baseline=cb,
+                   e2e={"value": cb["value"], "unit": "Gaussians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   gpu_launches=0, note="CPU oracle port (the reference ships no CPU path and oracle/_ref is unavailable here)")
+        print(json.dumps(out))
+        return 0
+
+    # ---- GPU arms ------------------------------------------------------------------------------------------------
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    P, V, W, H, F = wl["P"], wl["views"], wl["W"], wl["H"], wl["F"]
+    M = (SH_DEGREE + 1) ** 2
+    g, cams, cts = host_inputs(wl, rank, world)
+    G, C, T = to_device(g, cams, cts, torch)
+    impl = Impl(F, wl["depth"]) if a.impl == "ours" else RefImpl(F, wl["depth"])
+    flat, acc = make_packed(P, F, M, torch)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        Rtot = run_step(impl, G, C, T, flat, acc, dist)
+    if a.impl == "ours":
+        from manigaussian_b200 import _binding
+        _binding.profile_read()
+        _binding.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        Rtot = run_step(impl, G, C, T, flat, acc, dist)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    stages = None
+    if a.impl == "ours":
+        stages = _binding.profile_read()
+        _binding.profile_enable(False)
+    tmax = torch.tensor([ms], device="cuda")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    ms_step = ms / a.steps
+    value = P * V * world / (ms_step * 1e-3)
+
+    # ---- end-to-end leg through the public API, host buffers -----------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        Gh, Ch, Th = to_device(g, cams, cts, torch, pinned=True)
+        step = make_e2e(a.impl, wl, torch)
+        for _ in range(min(3, a.warmup)):
+            step(Gh, Ch, Th)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            step(Gh, Ch, Th)
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / a.steps], device="cuda")
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": P * V * world / float(te.item()), "unit": "Gaussians/s",
+               "h2d_bytes_per_step": int(nbytes(Gh) + sum(nbytes(c) for c in Ch) + sum(nbytes(t) for t in Th)),
+               "d2h_bytes_per_step": 4, "ms_per_step": float(te.item()) * 1e3,
+               "note": "wall clock around K steps incl. pinned H2D of all inputs, autograd module API, loss.item() D2H"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    from manigaussian_b200 import scenes
+    R_view = Rtot / V
+    N = W * H
+    balg_view = scenes.alg_bytes_per_view(P, R_view, N, M, F, depth=wl["depth"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    out = dict(base, value=value, ms_per_step=ms_step, config=cfg, clocks=clocks)
+    cfg.update(num_rendered_per_view=R_view, R_over_P=R_view / P, alg_bytes_per_view=balg_view,
+               pipeline_hbm_gbs=balg_view * V / (ms_step * 1e-3) / 1e9, pipeline_frac_of_peak=balg_view * V / (ms_step * 1e-3) / 1e9 / peak,
+               l2="no flush: per-step working set (inputs+state+grads, %.0f MB) exceeds the 126 MB L2" % (
+                   (P * (232 + 4 * (27 + F + 3 * M)) + 100 * R_view + 8 * N * (3 + F)) / 1e6))
+    if stages is not None:
+        per = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
+        cfg["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
+        hand = ("project_fwd", "emit_keys", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd")
+        out["gpu_launches"] = int(sum(stages[k][1] for k in hand))
+        cfg["library_launches_cub"] = "scan + radix sort (CUB) per view, not counted in gpu_launches"
+        dom = max(per, key=per.get)
+        Fp = F + (1 if wl["depth"] else 0)
+        live = P  # upper bound: every Gaussian's record/channel row touched once
+        alg = {
+            "blend_bwd": 4 * R_view + live * (32 + 4 * (3 + Fp)) + N * (4 * (3 + Fp) + 8) + P * 4 * (12 + F),
+            "blend_fwd": 4 * R_view + live * (32 + 4 * (3 + Fp)) + N * (4 * (3 + Fp) + 8),
+            "project_fwd": P * (44 + 12 * M + 4 + 32 + 4),
+            "project_bwd": P * (44 + 12 * M + 48 + 56 + 12 * M),
+            "sort": 2 * 12 * R_view, "emit_keys": P * 20 + 12 * R_view, "ranges_pack": R_view * (12 + 32) + 32 * R_view, "scan": 8 * P,
+        }[dom]
+        ach = alg / (per[dom] * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                           "traffic": None, "alg_bytes_per_launch": alg, "ms_per_launch": per[dom], "peak_source": peak_src,
+                           "note": "blend kernels are FP32-issue bound, not HBM bound (DESIGN.md)"}
+    else:
+        out["gpu_launches"] = 0
+        out["roofline"] = {"bound": "hbm", "kernel": "whole pipeline (reference kernels)", "achieved": cfg["pipeline_hbm_gbs"],
+                           "peak": peak, "unit": "GB/s", "frac": cfg["pipeline_frac_of_peak"], "traffic": None, "peak_source": peak_src}
+    if e2e is not None:
+        out["e2e"] = e2e
+    if a.gpus == 1 and not a.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline(wl)[0]
+        except Exception as ex:  # pragma: no cover
+            out["cpu_baseline"] = {"error": str(ex)}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,174 @@
+/*
+ * mgs_rasterizer.h -- C ABI of the B200-native differentiable Gaussian-splatting rasterizer.
+ *
+ * This is the drop-in boundary for ManiGaussian's rasterizer hot path.  Each entry point replaces one
+ * static method of the reference's raw-pointer C++ API, CudaRasterizer::Rasterizer
+ * (third_party/gaussian-splatting/submodules/diff-gaussian-rasterization/cuda_rasterizer/rasterizer.h:20-92,
+ * implemented in rasterizer_impl.cu), which the reference's torch glue (rasterize_points.cu:36-247) and pybind
+ * module (ext.cpp:14-18) wrap.  Plain C types only: device pointers, sizes, scalars, a CUDA stream handle
+ * as void*, and C function pointers where the reference passes std::function<char*(size_t)> allocators.
+ *
+ * Conventions shared with the reference:
+ *  - all arrays are fp32 device memory unless noted; a NULL pointer means "not provided"
+ *    (reference: forward.cu:206,242; backward.cu:390,394);
+ *  - viewmatrix / projmatrix are the 16-float row-vector (transposed) matrices read as m[4*col+row]
+ *    (auxiliary.h:58-77); tan_fov* are tan(fov/2);
+ *  - geom/binning/image state buffers are opaque bytes owned by the caller between forward and backward
+ *    (rasterizer_impl.h:29-65); their internal layout is private to this library.
+ * Differences (supersets) from the reference:
+ *  - F, the number of feature channels, is a RUN-TIME argument (0..32) instead of the compile-time
+ *    NUM_CHANNELS_language_feature (config.h:16); include_feature == (F > 0 && feature != NULL);
+ *  - an optional depth plane (out_depth / dL_dpix_depth) renders view-space z as one more blended channel;
+ *  - work is enqueued on `stream` (the reference uses the legacy default stream);
+ *  - outputs are fully overwritten: callers need not zero-initialise them.
+ *
+ * All functions return >= 0 on success and a negative MGS_ERR_* code on failure; mgs_last_error() returns a
+ * thread-local description.  No global state, no handles; re-entrant like the reference.
+ */
+#ifndef MGS_RASTERIZER_H
+#define MGS_RASTERIZER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGS_ERR_INVALID_ARG (-1)
+#define MGS_ERR_UNSUPPORTED (-2)
+#define MGS_ERR_CUDA (-3)
+#define MGS_ERR_ALLOC (-4)
+
+#define MGS_MAX_FEATURE_CHANNELS 32
+
+/* Allocator callback: return a device pointer to at least `bytes` bytes (any alignment >= 16; the library
+ * re-aligns to 128), or NULL.  Replaces std::function<char*(size_t)> (rasterizer.h:32-34). */
+typedef char* (*mgs_alloc_fn)(void* user, size_t bytes);
+
+/* Library / ABI version (major*100 + minor). */
+int mgs_abi_version(void);
+const char* mgs_last_error(void);
+
+/* Bytes the forward will request for the geometry (per-Gaussian) and image (per-pixel) state. */
+size_t mgs_geometry_state_bytes(int P);
+size_t mgs_image_state_bytes(int width, int height);
+size_t mgs_binning_state_bytes(int num_rendered);
+
+/*
+ * Forward.  Replaces CudaRasterizer::Rasterizer::forward (rasterizer.h:31-60, rasterizer_impl.cu:198-355).
+ * Returns num_rendered (R, the number of Gaussian/tile instances), which the caller passes to mgs_backward.
+ *   D = active SH degree, M = SH coefficients per Gaussian (0 when shs == NULL), F = feature channels.
+ *   out_color [3,H,W], out_feature [F,H,W] (ignored when F == 0), out_depth [H,W] or NULL, radii int32 [P].
+ * One stream synchronisation happens inside (R is read back to size the binning state), as in the reference
+ * (rasterizer_impl.cu:284).
+ */
+int mgs_forward(
+	mgs_alloc_fn geometry_alloc, void* geometry_user,
+	mgs_alloc_fn binning_alloc, void* binning_user,
+	mgs_alloc_fn image_alloc, void* image_user,
+	int P, int D, int M, int F,
+	const float* background,
+	int width, int height,
+	const float* means3D,
+	const float* shs,
+	const float* colors_precomp,
+	const float* feature_precomp,
+	const float* opacities,
+	const float* scales,
+	float scale_modifier,
+	const float* rotations,
+	const float* cov3D_precomp,
+	const float* viewmatrix,
+	const float* projmatrix,
+	const float* cam_pos,
+	float tan_fovx, float tan_fovy,
+	int prefiltered,
+	float* out_color,
+	float* out_feature,
+	float* out_depth,
+	int* radii,
+	int debug,
+	void* stream);
+
+/*
+ * Backward.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:62-91, rasterizer_impl.cu:359-463).
+ *   dL_dpix [3,H,W], dL_dpix_F [F,H,W] or NULL, dL_dpix_depth [H,W] or NULL.
+ *   Outputs (each fully written; NULL allowed for dL_dconic, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot):
+ *     dL_dmean2D [P,3], dL_dconic [P,4] (slots x,y,w like the reference's float4), dL_dopacity [P],
+ *     dL_dcolor [P,3], dL_dfeature [P,F], dL_dmean3D [P,3], dL_dcov3D [P,6], dL_dsh [P,M,3],
+ *     dL_dscale [P,3], dL_drot [P,4].
+ *   blend_scratch: device scratch of mgs_backward_scratch_bytes(P) bytes (contents irrelevant on entry).
+ */
+size_t mgs_backward_scratch_bytes(int P);
+int mgs_backward(
+	int P, int D, int M, int F, int R,
+	const float* background,
+	int width, int height,
+	const float* means3D,
+	const float* shs,
+	const float* colors_precomp,
+	const float* feature_precomp,
+	const float* scales,
+	float scale_modifier,
+	const float* rotations,
+	const float* cov3D_precomp,
+	const float* viewmatrix,
+	const float* projmatrix,
+	const float* campos,
+	float tan_fovx, float tan_fovy,
+	const int* radii,
+	char* geometry_state,
+	char* binning_state,
+	char* image_state,
+	const float* dL_dpix,
+	const float* dL_dpix_F,
+	const float* dL_dpix_depth,
+	float* dL_dmean2D,
+	float* dL_dconic,
+	float* dL_dopacity,
+	float* dL_dcolor,
+	float* dL_dfeature,
+	float* dL_dmean3D,
+	float* dL_dcov3D,
+	float* dL_dsh,
+	float* dL_dscale,
+	float* dL_drot,
+	char* blend_scratch,
+	int debug,
+	void* stream);
+
+/* Frustum test.  Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
+ * present: uint8 [P], 1 where view-space z > 0.2. */
+int mgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+	uint8_t* present, void* stream);
+
+/*
+ * Test/diagnostic access to the opaque state (used by the parity tests to compare stage by stage with the
+ * reference's GeometryState / BinningState / ImageState, rasterizer_impl.h:29-65).  Each call writes the
+ * device address of the named array inside the given state buffer; names:
+ *   geometry: "depths" f32[P], "means2D" f32[2P], "cov3D" f32[6P], "conic_opacity" f32[4P], "rgb" f32[3P],
+ *             "tiles_touched" u32[P], "point_offsets" u32[P], "clamped" u8[P] (3 bits), "extent" f32[2P]
+ *   binning : "point_list" u32[R], "point_list_keys" u64[R], "point_list_unsorted" u32[R],
+ *             "point_list_keys_unsorted" u64[R], "records" 32-byte records [R]
+ *   image   : "final_T" f32[N], "n_contrib" u32[N], "ranges" u32[2T]
+ * Returns 0, or MGS_ERR_INVALID_ARG for an unknown name.
+ */
+int mgs_state_array(const char* which_state, const char* name, char* state, int P_or_R_or_width, int height,
+	void** out_ptr);
+
+/*
+ * Measurement hooks (no reference counterpart; the reference's own timing code is commented out,
+ * forward.cu:416,433-437): when enabled, every stage launch is bracketed by CUDA events on the caller's
+ * stream.  mgs_profile_read sums the per-stage durations (ms) and launch counts recorded since the last
+ * read into arrays of mgs_profile_num_stages() entries and clears the record.
+ */
+int mgs_profile_enable(int on);
+int mgs_profile_num_stages(void);
+const char* mgs_profile_stage_name(int i);
+int mgs_profile_read(float* total_ms, int* counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGS_RASTERIZER_H */

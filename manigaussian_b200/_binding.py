@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI in include/mgs_rasterizer.h.
+
+The CUDA library is the product path: importing this module raises if it cannot be built or loaded.
+There is no CPU or PyTorch fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_c_float_p = C.c_void_p  # device pointers are passed as integers
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build()
+    if not os.path.exists(path):
+        raise ImportError(f"manigaussian_b200: CUDA library missing at {path}")
+    L = C.CDLL(path)
+    L.mgs_abi_version.restype = C.c_int
+    L.mgs_last_error.restype = C.c_char_p
+    for name in ("mgs_geometry_state_bytes", "mgs_binning_state_bytes", "mgs_backward_scratch_bytes"):
+        getattr(L, name).restype = C.c_size_t
+        getattr(L, name).argtypes = [C.c_int]
+    L.mgs_image_state_bytes.restype = C.c_size_t
+    L.mgs_image_state_bytes.argtypes = [C.c_int, C.c_int]
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.mgs_forward.restype = C.c_int
+    L.mgs_forward.argtypes = [ALLOC_FN, vp, ALLOC_FN, vp, ALLOC_FN, vp,
+                              i, i, i, i,            # P D M F
+                              vp, i, i,              # background, width, height
+                              vp, vp, vp, vp,        # means3D shs colors feature
+                              vp, vp, f, vp,         # opacities scales scale_modifier rotations
+                              vp, vp, vp, vp,        # cov3D_precomp viewmatrix projmatrix cam_pos
+                              f, f, i,               # tan_fovx tan_fovy prefiltered
+                              vp, vp, vp, vp,        # out_color out_feature out_depth radii
+                              i, vp]                 # debug stream
+    L.mgs_backward.restype = C.c_int
+    L.mgs_backward.argtypes = [i, i, i, i, i,        # P D M F R
+                               vp, i, i,             # background width height
+                               vp, vp, vp, vp,       # means3D shs colors feature
+                               vp, f, vp, vp,        # scales scale_modifier rotations cov3D_precomp
+                               vp, vp, vp, f, f,     # viewmatrix projmatrix campos tan_fovx tan_fovy
+                               vp, vp, vp, vp,       # radii geom binning image
+                               vp, vp, vp,           # dL_dpix dL_dpix_F dL_dpix_depth
+                               vp, vp, vp, vp, vp,   # dL_dmean2D dL_dconic dL_dopacity dL_dcolor dL_dfeature
+                               vp, vp, vp, vp, vp,   # dL_dmean3D dL_dcov3D dL_dsh dL_dscale dL_drot
+                               vp, i, vp]            # scratch debug stream
+    L.mgs_mark_visible.restype = C.c_int
+    L.mgs_mark_visible.argtypes = [i, vp, vp, vp, vp, vp]
+    L.mgs_state_array.restype = C.c_int
+    L.mgs_state_array.argtypes = [C.c_char_p, C.c_char_p, vp, i, i, C.POINTER(C.c_void_p)]
+    L.mgs_profile_enable.argtypes = [i]
+    L.mgs_profile_num_stages.restype = C.c_int
+    L.mgs_profile_stage_name.restype = C.c_char_p
+    L.mgs_profile_stage_name.argtypes = [i]
+    L.mgs_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    if L.mgs_abi_version() != 100:
+        raise ImportError("manigaussian_b200: ABI version mismatch")
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "mgs_abi_version", "mgs_last_error", "mgs_geometry_state_bytes", "mgs_image_state_bytes",
+    "mgs_binning_state_bytes", "mgs_backward_scratch_bytes", "mgs_forward", "mgs_backward",
+    "mgs_mark_visible", "mgs_state_array", "mgs_profile_enable", "mgs_profile_num_stages",
+    "mgs_profile_stage_name", "mgs_profile_read",
+)
+
+
+def profile_enable(on=True):
+    lib().mgs_profile_enable(int(bool(on)))
+
+
+def profile_read():
+    """{stage: (total_ms, launches)} since the last read."""
+    L = lib()
+    n = L.mgs_profile_num_stages()
+    ms, cnt = (C.c_float * n)(), (C.c_int * n)()
+    L.mgs_profile_read(ms, cnt)
+    return {L.mgs_profile_stage_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}
+
+
+def last_error():
+    return lib().mgs_last_error().decode()
+
+
+def check(rc, what):
+    if rc < 0:
+        raise RuntimeError(f"{what} failed ({rc}): {last_error()}")
+    return rc

@@ -1,0 +1,388 @@
+// C-ABI entry points (include/mgs_rasterizer.h): orchestration of the per-view forward and backward.
+//
+// Replaces CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+// (DGR/cuda_rasterizer/rasterizer_impl.cu:198-355, :359-463, :141-153).  Stage order and the meaning of
+// every argument follow the reference; the state-buffer layout, kernels and stream handling are ours.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/mgs_rasterizer.h"
+#include "mgs_common.cuh"
+#include "mgs_kernels.h"
+
+namespace mgs {
+int nq_for(int F);
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg)
+{
+	g_err = msg;
+	return code;
+}
+
+#define MGS_CUDA(call)                                                                                   \
+	do {                                                                                                 \
+		cudaError_t e_ = (call);                                                                         \
+		if (e_ != cudaSuccess)                                                                           \
+			return fail(MGS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+	} while (0)
+
+// after each stage: launch errors always, execution errors when debug (the reference's CHECK_CUDA, auxiliary.h:166-173)
+#define MGS_STAGE(name)                                                                                  \
+	do {                                                                                                 \
+		cudaError_t e_ = cudaGetLastError();                                                             \
+		if (e_ == cudaSuccess && debug) e_ = cudaStreamSynchronize(st);                                  \
+		if (e_ != cudaSuccess)                                                                           \
+			return fail(MGS_ERR_CUDA, std::string("stage ") + name + ": " + cudaGetErrorString(e_));     \
+	} while (0)
+
+// ---- optional per-stage CUDA-event timing (bench.py's roofline leg); off by default, zero cost when off ----
+enum Stage { ST_PROJECT_FWD = 0, ST_SCAN, ST_EMIT, ST_SORT, ST_RANGES_PACK, ST_BLEND_FWD, ST_BLEND_BWD, ST_PROJECT_BWD, ST_COUNT };
+struct StageEvt { int stage; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<StageEvt> g_prof_evts;
+struct StageTimer {
+	cudaStream_t st; bool on; StageEvt e;
+	StageTimer(int stage, cudaStream_t s) : st(s), on(g_prof_on)
+	{
+		if (!on) return;
+		e.stage = stage;
+		cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+		cudaEventRecord(e.a, st);
+	}
+	~StageTimer()
+	{
+		if (!on) return;
+		cudaEventRecord(e.b, st);
+		std::lock_guard<std::mutex> lk(g_prof_mu);
+		g_prof_evts.push_back(e);
+	}
+};
+
+template <typename T>
+static void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 128)
+{
+	size_t offset = (reinterpret_cast<uintptr_t>(chunk) + alignment - 1) & ~(alignment - 1);
+	ptr = reinterpret_cast<T*>(offset);
+	chunk = reinterpret_cast<char*>(ptr + count);
+}
+
+struct GeomState {
+	float* depths; uint8_t* clamped; float2* means2D; float* cov3D; float4* conic_opacity; float* rgb;
+	float2* extent; uint32_t* tiles_touched; uint32_t* point_offsets; char* scan_temp; size_t scan_bytes;
+	static GeomState carve(char*& chunk, size_t P)
+	{
+		GeomState g;
+		obtain(chunk, g.depths, P);
+		obtain(chunk, g.clamped, P);
+		obtain(chunk, g.means2D, P);
+		obtain(chunk, g.cov3D, P * 6);
+		obtain(chunk, g.conic_opacity, P);
+		obtain(chunk, g.rgb, P * 3);
+		obtain(chunk, g.extent, P);
+		obtain(chunk, g.tiles_touched, P);
+		obtain(chunk, g.point_offsets, P);
+		g.scan_bytes = scan_temp_bytes((int)P);
+		obtain(chunk, g.scan_temp, g.scan_bytes);
+		return g;
+	}
+};
+struct ImageState {
+	float* final_T; uint32_t* n_contrib; uint2* ranges;
+	static ImageState carve(char*& chunk, size_t N, size_t T)
+	{
+		ImageState s;
+		obtain(chunk, s.final_T, N);
+		obtain(chunk, s.n_contrib, N);
+		obtain(chunk, s.ranges, T);
+		return s;
+	}
+};
+struct BinState {
+	uint32_t* point_list; uint32_t* point_list_unsorted; uint64_t* keys; uint64_t* keys_unsorted; InstRec* recs;
+	char* sort_temp; size_t sort_bytes;
+	static BinState carve(char*& chunk, size_t R)
+	{
+		BinState b;
+		const size_t Rp = R + 8;  // slack so bulk copies of the last batch never run past the allocation
+		obtain(chunk, b.point_list, Rp);
+		obtain(chunk, b.point_list_unsorted, Rp);
+		obtain(chunk, b.keys, Rp);
+		obtain(chunk, b.keys_unsorted, Rp);
+		obtain(chunk, b.recs, Rp);
+		b.sort_bytes = sort_temp_bytes((int)R);
+		obtain(chunk, b.sort_temp, b.sort_bytes);
+		return b;
+	}
+};
+template <typename F>
+static size_t required(F carve)
+{
+	char* p = nullptr;
+	carve(p);
+	return reinterpret_cast<size_t>(p) + 128;
+}
+static size_t num_tiles(int W, int H) { return (size_t)ceil_div(W, TILE_X) * ceil_div(H, TILE_Y); }
+
+// next-highest bit of the MSB (number of bits needed for tile ids); same result as the reference's
+// getHigherMsb (rasterizer_impl.cu:35-50) for n >= 1
+static int higher_msb(uint32_t n)
+{
+	int bits = 0;
+	while (bits < 32 && (n >> bits)) bits++;
+	return bits;
+}
+
+}  // namespace mgs
+
+using namespace mgs;
+
+extern "C" {
+
+int mgs_abi_version(void) { return 100; }
+const char* mgs_last_error(void) { return g_err.c_str(); }
+
+size_t mgs_geometry_state_bytes(int P) { return required([&](char*& p) { GeomState::carve(p, (size_t)P); }); }
+size_t mgs_image_state_bytes(int width, int height)
+{
+	return required([&](char*& p) { ImageState::carve(p, (size_t)width * height, num_tiles(width, height)); });
+}
+size_t mgs_binning_state_bytes(int R) { return required([&](char*& p) { BinState::carve(p, (size_t)R); }); }
+size_t mgs_backward_scratch_bytes(int P) { return (size_t)P * GB_STRIDE * sizeof(float) + 128; }
+
+int mgs_forward(
+	mgs_alloc_fn geometry_alloc, void* geometry_user,
+	mgs_alloc_fn binning_alloc, void* binning_user,
+	mgs_alloc_fn image_alloc, void* image_user,
+	int P, int D, int M, int F,
+	const float* background, int width, int height,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* feature_precomp,
+	const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+	float tan_fovx, float tan_fovy, int prefiltered,
+	float* out_color, float* out_feature, float* out_depth, int* radii, int debug, void* stream)
+{
+	(void)prefiltered;  // the reference only uses it to trap on inconsistent input (auxiliary.h:156-160)
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	if (P < 0 || width <= 0 || height <= 0) return fail(MGS_ERR_INVALID_ARG, "bad P/width/height");
+	if (!geometry_alloc || !binning_alloc || !image_alloc) return fail(MGS_ERR_INVALID_ARG, "allocator callbacks are required");
+	if (!out_color || !background) return fail(MGS_ERR_INVALID_ARG, "out_color/background are required");
+	if (F < 0 || F > MGS_MAX_FEATURE_CHANNELS || !blend_supported(F))
+		return fail(MGS_ERR_UNSUPPORTED, "feature channel count must be in [0, 32]");
+	if (F > 0 && (!feature_precomp || !out_feature)) F = 0;  // include_feature == false
+	const size_t N = (size_t)width * height;
+	if (P == 0) {
+		// reference: outputs keep their zero fill when there are no Gaussians (rasterize_points.cu:70-92)
+		MGS_CUDA(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), st));
+		if (F > 0) MGS_CUDA(cudaMemsetAsync(out_feature, 0, (size_t)F * N * sizeof(float), st));
+		if (out_depth) MGS_CUDA(cudaMemsetAsync(out_depth, 0, N * sizeof(float), st));
+		return 0;
+	}
+	if (!means3D || !opacities || !viewmatrix || !projmatrix || !radii)
+		return fail(MGS_ERR_INVALID_ARG, "means3D/opacities/viewmatrix/projmatrix/radii are required");
+	if (!colors_precomp && !shs) return fail(MGS_ERR_INVALID_ARG, "provide SHs or precomputed colours");
+	if (!colors_precomp && !cam_pos) return fail(MGS_ERR_INVALID_ARG, "cam_pos is required with SHs");
+	if (!cov3D_precomp && (!scales || !rotations)) return fail(MGS_ERR_INVALID_ARG, "provide scales+rotations or a precomputed 3D covariance");
+
+	const float focal_y = height / (2.0f * tan_fovy);  // rasterizer_impl.cu:225-226
+	const float focal_x = width / (2.0f * tan_fovx);
+	const int gx = ceil_div(width, TILE_X), gy = ceil_div(height, TILE_Y);
+	const size_t T = (size_t)gx * gy;
+
+	char* gchunk = geometry_alloc(geometry_user, mgs_geometry_state_bytes(P));
+	char* ichunk = image_alloc(image_user, mgs_image_state_bytes(width, height));
+	if (!gchunk || !ichunk) return fail(MGS_ERR_ALLOC, "state allocation failed");
+	GeomState geom = GeomState::carve(gchunk, (size_t)P);
+	ImageState img = ImageState::carve(ichunk, N, T);
+
+	ProjectFwdArgs pa{};
+	pa.P = P; pa.D = D; pa.M = M;
+	pa.means3D = means3D; pa.scales = scales; pa.scale_modifier = scale_modifier; pa.rotations = rotations;
+	pa.opacities = opacities; pa.shs = shs; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
+	pa.viewmatrix = viewmatrix; pa.projmatrix = projmatrix; pa.cam_pos = cam_pos;
+	pa.W = width; pa.H = height; pa.tan_fovx = tan_fovx; pa.tan_fovy = tan_fovy; pa.focal_x = focal_x; pa.focal_y = focal_y;
+	pa.grid_x = gx; pa.grid_y = gy;
+	pa.radii = radii; pa.means2D = geom.means2D; pa.depths = geom.depths; pa.cov3D = geom.cov3D; pa.rgb = geom.rgb;
+	pa.conic_opacity = geom.conic_opacity; pa.extent = geom.extent; pa.clamped = geom.clamped; pa.tiles_touched = geom.tiles_touched;
+	{ StageTimer t_(ST_PROJECT_FWD, st); launch_project_fwd(pa, st); }
+	MGS_STAGE("project_fwd");
+
+	{ StageTimer t_(ST_SCAN, st); launch_scan(geom.scan_temp, geom.scan_bytes, geom.tiles_touched, geom.point_offsets, P, st); }
+	MGS_STAGE("scan");
+
+	int num_rendered = 0;
+	MGS_CUDA(cudaMemcpyAsync(&num_rendered, geom.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+	MGS_CUDA(cudaStreamSynchronize(st));
+	if (num_rendered < 0) return fail(MGS_ERR_UNSUPPORTED, "more than 2^31-1 tile instances");
+
+	char* bchunk = binning_alloc(binning_user, mgs_binning_state_bytes(num_rendered));
+	if (!bchunk) return fail(MGS_ERR_ALLOC, "binning state allocation failed");
+	BinState bin = BinState::carve(bchunk, (size_t)num_rendered);
+
+	{ StageTimer t_(ST_EMIT, st); launch_emit_keys(P, geom.means2D, geom.depths, geom.point_offsets, radii, gx, gy, bin.keys_unsorted, bin.point_list_unsorted, st); }
+	MGS_STAGE("emit_keys");
+	if (num_rendered > 0) {
+		const int bit = higher_msb((uint32_t)T);
+		StageTimer t_(ST_SORT, st);
+		launch_sort_pairs(bin.sort_temp, bin.sort_bytes, bin.keys_unsorted, bin.keys, bin.point_list_unsorted, bin.point_list,
+			num_rendered, 32 + bit, st);
+		MGS_STAGE("sort");
+	}
+	{
+		StageTimer t_(ST_RANGES_PACK, st);
+		launch_ranges_and_pack(num_rendered, (int)T, bin.keys, bin.point_list, geom.means2D, geom.conic_opacity, geom.extent,
+			img.ranges, bin.recs, st);
+	}
+	MGS_STAGE("ranges_pack");
+
+	BlendArgs ba{};
+	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F; ba.nq = nq_for(F);
+	ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
+	ba.rgb = colors_precomp ? colors_precomp : geom.rgb;
+	ba.depths = geom.depths; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
+	ba.want_depth = out_depth != nullptr;
+	ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
+	ba.out_color = out_color; ba.out_feature = out_feature; ba.out_depth = out_depth;
+	{ StageTimer t_(ST_BLEND_FWD, st); launch_blend_fwd(ba, st); }
+	MGS_STAGE("blend_fwd");
+	return num_rendered;
+}
+
+int mgs_backward(
+	int P, int D, int M, int F, int R,
+	const float* background, int width, int height,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* feature_precomp,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	const float* viewmatrix, const float* projmatrix, const float* campos, float tan_fovx, float tan_fovy,
+	const int* radii, char* geometry_state, char* binning_state, char* image_state,
+	const float* dL_dpix, const float* dL_dpix_F, const float* dL_dpix_depth,
+	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dfeature,
+	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+	char* blend_scratch, int debug, void* stream)
+{
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	if (P < 0 || width <= 0 || height <= 0 || R < 0) return fail(MGS_ERR_INVALID_ARG, "bad P/R/width/height");
+	if (P == 0) return 0;
+	if (F < 0 || F > MGS_MAX_FEATURE_CHANNELS) return fail(MGS_ERR_UNSUPPORTED, "feature channel count must be in [0, 32]");
+	if (F > 0 && (!feature_precomp || !dL_dpix_F || !dL_dfeature)) F = 0;
+	if (!geometry_state || !binning_state || !image_state || !blend_scratch)
+		return fail(MGS_ERR_INVALID_ARG, "state buffers and scratch are required");
+	if (!dL_dpix || !dL_dmean2D || !dL_dopacity || !dL_dmean3D || !means3D || !radii || !background)
+		return fail(MGS_ERR_INVALID_ARG, "required pointer is NULL");
+	const float focal_y = height / (2.0f * tan_fovy);
+	const float focal_x = width / (2.0f * tan_fovx);
+	const int gx = ceil_div(width, TILE_X), gy = ceil_div(height, TILE_Y);
+	const size_t N = (size_t)width * height, T = (size_t)gx * gy;
+
+	GeomState geom = GeomState::carve(geometry_state, (size_t)P);
+	BinState bin = BinState::carve(binning_state, (size_t)R);
+	ImageState img = ImageState::carve(image_state, N, T);
+
+	float* gb = nullptr;
+	obtain(blend_scratch, gb, (size_t)P * GB_STRIDE);
+	MGS_CUDA(cudaMemsetAsync(gb, 0, (size_t)P * GB_STRIDE * sizeof(float), st));
+	if (F > 0) MGS_CUDA(cudaMemsetAsync(dL_dfeature, 0, (size_t)P * F * sizeof(float), st));
+
+	BlendArgs ba{};
+	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F; ba.nq = nq_for(F);
+	ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
+	ba.rgb = colors_precomp ? colors_precomp : geom.rgb;
+	ba.depths = geom.depths; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
+	ba.want_depth = dL_dpix_depth != nullptr;
+	ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
+	ba.dL_dcolor = dL_dpix; ba.dL_dfeature = F > 0 ? dL_dpix_F : nullptr; ba.dL_ddepth = dL_dpix_depth;
+	ba.gb = gb; ba.dL_dfeat = F > 0 ? dL_dfeature : nullptr;
+	if (R > 0) {
+		{ StageTimer t_(ST_BLEND_BWD, st); launch_blend_bwd(ba, st); }
+		MGS_STAGE("blend_bwd");
+	}
+
+	ProjectBwdArgs pb{};
+	pb.P = P; pb.D = D; pb.M = M;
+	pb.means3D = means3D; pb.radii = radii; pb.shs = shs; pb.clamped = geom.clamped;
+	pb.scales = scales; pb.rotations = rotations; pb.scale_modifier = scale_modifier;
+	pb.cov3D = geom.cov3D; pb.cov3D_precomp = cov3D_precomp;
+	pb.viewmatrix = viewmatrix; pb.projmatrix = projmatrix; pb.cam_pos = campos;
+	pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy; pb.focal_x = focal_x; pb.focal_y = focal_y;
+	pb.gb = gb;
+	pb.dL_dmean2D = dL_dmean2D; pb.dL_dconic = dL_dconic; pb.dL_dopacity = dL_dopacity; pb.dL_dcolor = dL_dcolor;
+	pb.dL_dmean3D = dL_dmean3D; pb.dL_dcov3D = dL_dcov3D; pb.dL_dsh = shs ? dL_dsh : nullptr;
+	pb.dL_dscale = dL_dscale; pb.dL_drot = dL_drot; pb.dL_ddepth = nullptr;
+	if (shs && !dL_dsh) pb.shs = nullptr;
+	if (!scales || !rotations || !dL_dscale || !dL_drot) { pb.scales = nullptr; }
+	{ StageTimer t_(ST_PROJECT_BWD, st); launch_project_bwd(pb, st); }
+	MGS_STAGE("project_bwd");
+	return 0;
+}
+
+int mgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present, void* stream)
+{
+	(void)projmatrix;
+	if (P < 0) return fail(MGS_ERR_INVALID_ARG, "bad P");
+	if (P == 0) return 0;
+	if (!means3D || !viewmatrix || !present) return fail(MGS_ERR_INVALID_ARG, "required pointer is NULL");
+	launch_mark_visible(P, means3D, viewmatrix, present, reinterpret_cast<cudaStream_t>(stream));
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(MGS_ERR_CUDA, cudaGetErrorString(e));
+	return 0;
+}
+
+int mgs_profile_enable(int on)
+{
+	std::lock_guard<std::mutex> lk(g_prof_mu);
+	g_prof_on = on != 0;
+	return 0;
+}
+
+// Sums the recorded stage durations (ms) and launch counts since the last call, then clears them.
+// total_ms / counts: arrays of mgs_profile_num_stages() entries.  Synchronises on the recorded events.
+int mgs_profile_num_stages(void) { return ST_COUNT; }
+const char* mgs_profile_stage_name(int i)
+{
+	static const char* names[ST_COUNT] = { "project_fwd", "scan", "emit_keys", "sort", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd" };
+	return (i >= 0 && i < ST_COUNT) ? names[i] : "";
+}
+int mgs_profile_read(float* total_ms, int* counts)
+{
+	std::lock_guard<std::mutex> lk(g_prof_mu);
+	for (int i = 0; i < ST_COUNT; i++) { total_ms[i] = 0.f; counts[i] = 0; }
+	for (auto& e : g_prof_evts) {
+		float ms = 0.f;
+		cudaEventSynchronize(e.b);
+		if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { total_ms[e.stage] += ms; counts[e.stage]++; }
+		cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+	}
+	g_prof_evts.clear();
+	return 0;
+}
+
+int mgs_state_array(const char* which_state, const char* name, char* state, int a0, int a1, void** out_ptr)
+{
+	if (!which_state || !name || !state || !out_ptr) return fail(MGS_ERR_INVALID_ARG, "NULL argument");
+	const std::string w(which_state), n(name);
+	void* p = nullptr;
+	if (w == "geometry") {
+		GeomState g = GeomState::carve(state, (size_t)a0);
+		if (n == "depths") p = g.depths; else if (n == "means2D") p = g.means2D; else if (n == "cov3D") p = g.cov3D;
+		else if (n == "conic_opacity") p = g.conic_opacity; else if (n == "rgb") p = g.rgb;
+		else if (n == "tiles_touched") p = g.tiles_touched; else if (n == "point_offsets") p = g.point_offsets;
+		else if (n == "clamped") p = g.clamped; else if (n == "extent") p = g.extent;
+	} else if (w == "binning") {
+		BinState b = BinState::carve(state, (size_t)a0);
+		if (n == "point_list") p = b.point_list; else if (n == "point_list_keys") p = b.keys;
+		else if (n == "point_list_unsorted") p = b.point_list_unsorted; else if (n == "point_list_keys_unsorted") p = b.keys_unsorted;
+		else if (n == "records") p = b.recs;
+	} else if (w == "image") {
+		ImageState s = ImageState::carve(state, (size_t)a0 * a1, num_tiles(a0, a1));
+		if (n == "final_T") p = s.final_T; else if (n == "n_contrib") p = s.n_contrib; else if (n == "ranges") p = s.ranges;
+	}
+	if (!p) return fail(MGS_ERR_INVALID_ARG, "unknown state array " + w + "/" + n);
+	*out_ptr = p;
+	return 0;
+}
+
+}  // extern "C"

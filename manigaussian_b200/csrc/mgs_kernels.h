@@ -1,0 +1,116 @@
+// Internal launch interface between the C-ABI (api.cu) and the kernels.  Plain structs of raw pointers.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mgs {
+
+struct InstRec;
+
+struct ProjectFwdArgs {
+	int P, D, M;
+	const float* means3D;
+	const float* scales;
+	float scale_modifier;
+	const float* rotations;
+	const float* opacities;
+	const float* shs;
+	const float* cov3D_precomp;
+	const float* colors_precomp;
+	const float* viewmatrix;
+	const float* projmatrix;
+	const float* cam_pos;
+	int W, H;
+	float tan_fovx, tan_fovy, focal_x, focal_y;
+	uint32_t grid_x, grid_y;
+	// outputs
+	int* radii;
+	float2* means2D;
+	float* depths;
+	float* cov3D;
+	float* rgb;
+	float4* conic_opacity;
+	float2* extent;
+	uint8_t* clamped;  // 3 bits per Gaussian
+	uint32_t* tiles_touched;
+};
+
+struct ProjectBwdArgs {
+	int P, D, M;
+	const float* means3D;
+	const int* radii;
+	const float* shs;
+	const uint8_t* clamped;
+	const float* scales;
+	const float* rotations;
+	float scale_modifier;
+	const float* cov3D;          // state copy computed by the forward
+	const float* cov3D_precomp;  // or the user's
+	const float* viewmatrix;
+	const float* projmatrix;
+	const float* cam_pos;
+	float tan_fovx, tan_fovy, focal_x, focal_y;
+	const float* gb;  // [P, GB_STRIDE] blend-stage gradients
+	// outputs (each row written exactly once; nullable where noted)
+	float* dL_dmean2D;  // [P,3]
+	float* dL_dconic;   // [P,4] nullable
+	float* dL_dopacity; // [P]
+	float* dL_dcolor;   // [P,3] nullable
+	float* dL_dmean3D;  // [P,3]
+	float* dL_dcov3D;   // [P,6] nullable
+	float* dL_dsh;      // [P,M,3] nullable
+	float* dL_dscale;   // [P,3] nullable
+	float* dL_drot;     // [P,4] nullable
+	float* dL_ddepth;   // [P] nullable
+};
+
+struct BlendArgs {
+	int W, H;
+	int grid_x, grid_y;
+	int F;                       // user feature channels (0 = none)
+	int nq;                      // float4 groups per channel row: ceil((4 + F) / 4)
+	const uint2* ranges;         // [T]
+	const uint32_t* point_list;  // [R] sorted Gaussian ids
+	const InstRec* recs;         // [R] sorted packed records
+	const float* rgb;            // [P,3]
+	const float* depths;         // [P]
+	const float* feature;        // [P,F] or null
+	const float* bg;             // [3]
+	int want_depth;
+	// forward outputs / backward inputs
+	float* final_T;              // [N]
+	uint32_t* n_contrib;         // [N]
+	float* out_color;            // [3,H,W]
+	float* out_feature;          // [F,H,W]
+	float* out_depth;            // [H,W] nullable
+	// backward only
+	const float* dL_dcolor;      // [3,H,W]
+	const float* dL_dfeature;    // [F,H,W] nullable
+	const float* dL_ddepth;      // [H,W] nullable
+	float* gb;                   // [P,GB_STRIDE] (zeroed by caller)
+	float* dL_dfeat;             // [P,F] (zeroed by caller) nullable
+};
+
+void launch_project_fwd(const ProjectFwdArgs& a, cudaStream_t s);
+void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s);
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
+
+// binning.cu
+size_t scan_temp_bytes(int P);
+size_t sort_temp_bytes(int R);
+void launch_scan(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int P, cudaStream_t s);
+void launch_emit_keys(int P, const float2* means2D, const float* depths, const uint32_t* offsets, const int* radii,
+	uint32_t grid_x, uint32_t grid_y, uint64_t* keys, uint32_t* values, cudaStream_t s);
+void launch_sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
+	const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit, cudaStream_t s);
+void launch_ranges_and_pack(int R, int num_tiles, const uint64_t* keys, const uint32_t* point_list,
+	const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs, cudaStream_t s);
+
+// blend_fwd.cu / blend_bwd.cu
+int blend_supported(int F);
+int nq_for(int F);
+void launch_blend_fwd(const BlendArgs& a, cudaStream_t s);
+void launch_blend_bwd(const BlendArgs& a, cudaStream_t s);
+
+}  // namespace mgs

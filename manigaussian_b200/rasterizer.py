@@ -1,0 +1,305 @@
+"""Host-side mirror of the reference's Python operator for the rasterizer hot path.
+
+Same names, argument order, return values and error behaviour as
+DGR/diff_gaussian_rasterization/__init__.py (GaussianRasterizationSettings :166-179,
+GaussianRasterizer :181-233, _RasterizeGaussians :46-164) and the pybind functions of DGR/ext.cpp:14-18
+(rasterize_gaussians / rasterize_gaussians_backward / mark_visible, DGR/rasterize_points.cu:36-247), so that
+ManiGaussian's agents/manigaussian_bc/gaussian_renderer/__init__.py:14-94 runs unchanged.  PyTorch is used for
+device memory, streams and autograd plumbing only; all computation happens in the sm_100a library behind
+include/mgs_rasterizer.h.
+
+Supersets of the reference: the feature width F is read from the tensor at run time (0..32) instead of being
+compiled in (config.h:16), and `return_depth=True` adds a view-space depth plane.
+"""
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _binding as _b
+
+
+def _ptr(t):
+    """Device pointer of a tensor; None / empty tensor -> NULL (the reference's `data_ptr() == nullptr`)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _prep(t, device):
+    """float32, contiguous, on `device` (the reference calls .contiguous() on every input, rasterize_points.cu:104-125)."""
+    if t is None:
+        return None
+    if t.numel() == 0:
+        return t
+    if t.dtype != torch.float32 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+class _Alloc:
+    """Allocator callback backed by torch's caching allocator (replaces resizeFunctional, rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+
+        def _cb(_user, nbytes):
+            self.tensor = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
+            return self.tensor.data_ptr()
+
+        self.fn = _b.ALLOC_FN(_cb)
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def rasterize_gaussians_raw(bg, means3D, colors, language_feature, opacity, scales, rotations, scale_modifier,
+                            cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
+                            sh, degree, campos, prefiltered, debug, include_feature, return_depth=False):
+    """Same contract as the reference's `_C.rasterize_gaussians` (DGR/rasterize_points.cu:36-128).
+
+    Returns (num_rendered, color [3,H,W], feature [F,H,W] or [1], radii [P] int32, geomBuffer, binningBuffer,
+    imgBuffer) and, when return_depth, an extra trailing depth [H,W] tensor.
+    """
+    if means3D.ndimension() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("manigaussian_b200 runs on CUDA tensors only (there is no CPU path)")
+    L = _b.lib()
+    dev = means3D.device
+    P, H, W = means3D.size(0), int(image_height), int(image_width)
+    means3D, colors, language_feature, opacity = (_prep(x, dev) for x in (means3D, colors, language_feature, opacity))
+    scales, rotations, cov3D_precomp, sh = (_prep(x, dev) for x in (scales, rotations, cov3D_precomp, sh))
+    bg, viewmatrix, projmatrix, campos = (_prep(x, dev) for x in (bg, viewmatrix, projmatrix, campos))
+    F = 0
+    if include_feature and language_feature is not None and language_feature.numel() > 0:
+        F = language_feature.size(1)
+    M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
+    out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    out_feature = torch.empty((F, H, W), dtype=torch.float32, device=dev) if include_feature else \
+        torch.zeros((1,), dtype=torch.float32, device=dev)
+    out_depth = torch.empty((H, W), dtype=torch.float32, device=dev) if return_depth else None
+    radii = torch.empty((P,), dtype=torch.int32, device=dev)
+    ga, ba, ia = _Alloc(dev), _Alloc(dev), _Alloc(dev)
+    rendered = 0
+    if P != 0:
+        with torch.cuda.device(dev):
+            rendered = _b.check(L.mgs_forward(
+                ga.fn, None, ba.fn, None, ia.fn, None,
+                P, int(degree), M, F,
+                _ptr(bg), W, H,
+                _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(language_feature) if F else None,
+                _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
+                float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
+                _ptr(out_color), _ptr(out_feature) if F else None, _ptr(out_depth), _ptr(radii),
+                int(bool(debug)), _stream(dev)), "mgs_forward")
+    else:
+        out_color.zero_()
+        if include_feature:
+            out_feature.zero_()
+        if out_depth is not None:
+            out_depth.zero_()
+    ret = (rendered, out_color, out_feature, radii, ga.tensor, ba.tensor, ia.tensor)
+    return ret + (out_depth,) if return_depth else ret
+
+
+def rasterize_gaussians_backward_raw(bg, means3D, radii, colors, language_feature, scales, rotations, scale_modifier,
+                                     cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
+                                     dL_dout_language_feature, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                     imageBuffer, debug, include_feature, dL_dout_depth=None):
+    """Same contract as the reference's `_C.rasterize_gaussians_backward` (DGR/rasterize_points.cu:131-225):
+    returns (dL_dmeans2D, dL_dcolors, dL_dlanguage_feature, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh,
+    dL_dscales, dL_drotations)."""
+    L = _b.lib()
+    dev = means3D.device
+    P = means3D.size(0)
+    H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+    means3D, colors, language_feature = (_prep(x, dev) for x in (means3D, colors, language_feature))
+    scales, rotations, cov3D_precomp, sh = (_prep(x, dev) for x in (scales, rotations, cov3D_precomp, sh))
+    bg, viewmatrix, projmatrix, campos = (_prep(x, dev) for x in (bg, viewmatrix, projmatrix, campos))
+    dL_dout_color = _prep(dL_dout_color, dev)
+    dL_dout_depth = _prep(dL_dout_depth, dev)
+    F = 0
+    if include_feature and language_feature is not None and language_feature.numel() > 0:
+        F = language_feature.size(1)
+        dL_dout_language_feature = _prep(dL_dout_language_feature, dev)
+    M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
+    opts = dict(dtype=torch.float32, device=dev)
+    dL_dmeans3D = torch.empty((P, 3), **opts)
+    dL_dmeans2D = torch.empty((P, 3), **opts)
+    dL_dcolors = torch.empty((P, 3), **opts)
+    dL_dfeature = torch.empty((P, F), **opts) if F else torch.zeros((1,), **opts)
+    dL_dopacity = torch.empty((P, 1), **opts)
+    dL_dcov3D = torch.empty((P, 6), **opts)
+    dL_dsh = torch.empty((P, M, 3), **opts)
+    dL_dscales = torch.empty((P, 3), **opts)
+    dL_drotations = torch.empty((P, 4), **opts)
+    if P != 0:
+        scratch = torch.empty((L.mgs_backward_scratch_bytes(P),), dtype=torch.uint8, device=dev)
+        has_sr = scales is not None and scales.numel() != 0
+        with torch.cuda.device(dev):
+            _b.check(L.mgs_backward(
+                P, int(degree), M, F, int(R),
+                _ptr(bg), W, H,
+                _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(language_feature) if F else None,
+                _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
+                _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                _ptr(dL_dout_color), _ptr(dL_dout_language_feature) if F else None, _ptr(dL_dout_depth),
+                _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dfeature) if F else None,
+                _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh) if M else None,
+                _ptr(dL_dscales) if has_sr else None, _ptr(dL_drotations) if has_sr else None,
+                _ptr(scratch), int(bool(debug)), _stream(dev)), "mgs_backward")
+        if not has_sr:
+            dL_dscales.zero_()
+            dL_drotations.zero_()
+    return (dL_dmeans2D, dL_dcolors, dL_dfeature, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+
+
+def mark_visible_raw(means3D, viewmatrix, projmatrix):
+    """Same contract as the reference's `_C.mark_visible` (DGR/rasterize_points.cu:227-247)."""
+    L = _b.lib()
+    dev = means3D.device
+    P = means3D.size(0)
+    means3D, viewmatrix, projmatrix = (_prep(x, dev) for x in (means3D, viewmatrix, projmatrix))
+    present = torch.zeros((P,), dtype=torch.uint8, device=dev)
+    if P != 0:
+        with torch.cuda.device(dev):
+            _b.check(L.mgs_mark_visible(P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix), _ptr(present), _stream(dev)),
+                     "mgs_mark_visible")
+    return present.bool()
+
+
+def state_array(which, name, state, a0, a1=0):
+    """Device address of a named array inside an opaque state buffer (tests only)."""
+    import ctypes
+    out = ctypes.c_void_p()
+    _b.check(_b.lib().mgs_state_array(which.encode(), name.encode(), state.data_ptr(), int(a0), int(a1), ctypes.byref(out)),
+             "mgs_state_array")
+    return out.value
+
+
+def cpu_deep_copy_tuple(input_tuple):
+    return tuple(item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, language_feature_precomp, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings, return_depth=False):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, language_feature_precomp, opacities, scales,
+                                     rotations, cov3Ds_precomp, raster_settings, return_depth)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, language_feature_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings, return_depth=False):
+        s = raster_settings
+        args = (s.bg, means3D, colors_precomp, language_feature_precomp, opacities, scales, rotations, s.scale_modifier,
+                cov3Ds_precomp, s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.image_height, s.image_width, sh,
+                s.sh_degree, s.campos, s.prefiltered, s.debug, s.include_feature)
+        if s.debug:
+            cpu_args = cpu_deep_copy_tuple(args)  # copy before they can be corrupted
+            try:
+                out = rasterize_gaussians_raw(*args, return_depth=return_depth)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            out = rasterize_gaussians_raw(*args, return_depth=return_depth)
+        num_rendered, color, language_feature, radii, geomBuffer, binningBuffer, imgBuffer = out[:7]
+        depth = out[7] if return_depth else None
+        ctx.raster_settings = s
+        ctx.num_rendered = num_rendered
+        ctx.return_depth = return_depth
+        ctx.save_for_backward(colors_precomp, language_feature_precomp, means3D, scales, rotations, cov3Ds_precomp, radii,
+                              sh, geomBuffer, binningBuffer, imgBuffer)
+        ctx.mark_non_differentiable(radii)
+        if return_depth:
+            return color, language_feature, radii, depth
+        return color, language_feature, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_out_language_feature, _radii=None, grad_out_depth=None):
+        s = ctx.raster_settings
+        (colors_precomp, language_feature_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
+         binningBuffer, imgBuffer) = ctx.saved_tensors
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((3, s.image_height, s.image_width), dtype=torch.float32, device=means3D.device)
+        if s.include_feature and grad_out_language_feature is None:
+            grad_out_language_feature = torch.zeros((language_feature_precomp.size(1), s.image_height, s.image_width),
+                                                    dtype=torch.float32, device=means3D.device)
+        args = (s.bg, means3D, radii, colors_precomp, language_feature_precomp, scales, rotations, s.scale_modifier,
+                cov3Ds_precomp, s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, grad_out_color,
+                grad_out_language_feature, sh, s.sh_degree, s.campos, geomBuffer, ctx.num_rendered, binningBuffer,
+                imgBuffer, s.debug, s.include_feature)
+        depth_grad = grad_out_depth if ctx.return_depth else None
+        if s.debug:
+            cpu_args = cpu_deep_copy_tuple(args)
+            try:
+                grads = rasterize_gaussians_backward_raw(*args, dL_dout_depth=depth_grad)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            grads = rasterize_gaussians_backward_raw(*args, dL_dout_depth=depth_grad)
+        (grad_means2D, grad_colors_precomp, grad_language_feature_precomp, grad_opacities, grad_means3D,
+         grad_cov3Ds_precomp, grad_sh, grad_scales, grad_rotations) = grads
+
+        def _or_none(g, inp):
+            return g if (inp is not None and inp.numel() != 0) else None
+
+        return (grad_means3D, grad_means2D, _or_none(grad_sh, sh), _or_none(grad_colors_precomp, colors_precomp),
+                _or_none(grad_language_feature_precomp, language_feature_precomp) if s.include_feature else None,
+                grad_opacities, _or_none(grad_scales, scales), _or_none(grad_rotations, rotations),
+                _or_none(grad_cov3Ds_precomp, cov3Ds_precomp), None, None)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    include_feature: bool
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings, return_depth=False):
+        super().__init__()
+        self.raster_settings = raster_settings
+        self.return_depth = return_depth
+
+    def markVisible(self, positions):
+        # Mark visible points (based on frustum culling for camera) with a boolean
+        with torch.no_grad():
+            s = self.raster_settings
+            return mark_visible_raw(positions, s.viewmatrix, s.projmatrix)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, language_feature_precomp=None,
+                scales=None, rotations=None, cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        empty = torch.Tensor([])
+        shs = empty if shs is None else shs
+        colors_precomp = empty if colors_precomp is None else colors_precomp
+        language_feature_precomp = empty if language_feature_precomp is None else language_feature_precomp
+        scales = empty if scales is None else scales
+        rotations = empty if rotations is None else rotations
+        cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, language_feature_precomp, opacities, scales,
+                                   rotations, cov3D_precomp, self.raster_settings, self.return_depth)
