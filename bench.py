@@ -194,15 +194,9 @@ PACKED = ("dL_dmeans3D", "dL_dmeans2D", "dL_dscales", "dL_drotations", "dL_dopac
 
 def make_packed(P, F, M, torch):
     """One flat fp32 buffer holding every per-Gaussian gradient the optimiser needs; the all-reduce message."""
-    widths = dict(dL_dmeans3D=3, dL_dmeans2D=3, dL_dscales=3, dL_drotations=4, dL_dopacity=1, dL_dsh=3 * M, dL_dfeature=F)
-    flat = torch.zeros(P * sum(widths.values()), device="cuda")
-    views, off = {}, 0
-    for k in PACKED:
-        n = P * widths[k]
-        if n:
-            views[k] = flat[off:off + n].view(P, widths[k])
-        off += n
-    return flat, views
+    from manigaussian_b200.parallel import PackedGradients
+    pk = PackedGradients(P, F, M, "cuda")
+    return pk.flat, pk.views
 
 
 def run_step(impl, G, C, T, flat, acc, dist=None):

@@ -1,0 +1,48 @@
+"""View-parallel multi-GPU plumbing.
+
+The rasterizer shards by VIEW: Gaussians are replicated on every rank, each rank renders its own views, and the only
+exchange is one SUM all-reduce of the per-Gaussian gradients.  All gradient tensors the optimiser consumes live in ONE
+flat fp32 buffer (`PackedGradients.flat`) so that the exchange is a single collective on a single message:
+  [means3D 3 | means2D 3 | scales 3 | rotations 4 | opacity 1 | SH 3M | features F] x P   (232 B/Gaussian at M=4, F=32).
+The reference has no counterpart: it renders one view per call on one GPU and lets DDP all-reduce MLP parameters
+(train.py:92-105); Gaussians never cross GPUs there.
+"""
+import torch
+
+FIELDS = ("dL_dmeans3D", "dL_dmeans2D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dsh", "dL_dfeature")
+
+
+def shard_views(total_views, rank, world):
+    """Round-robin view ownership: view v belongs to rank v % world."""
+    return [v for v in range(total_views) if v % world == rank]
+
+
+class PackedGradients:
+    def __init__(self, P, F, M, device):
+        self.widths = dict(dL_dmeans3D=3, dL_dmeans2D=3, dL_dscales=3, dL_drotations=4, dL_dopacity=1, dL_dsh=3 * M, dL_dfeature=F)
+        self.P = P
+        self.flat = torch.zeros(P * sum(self.widths.values()), dtype=torch.float32, device=device)
+        self.views, off = {}, 0
+        for k in FIELDS:
+            n = P * self.widths[k]
+            if n:
+                self.views[k] = self.flat[off:off + n].view(P, self.widths[k])
+            off += n
+
+    @property
+    def bytes_per_gaussian(self):
+        return 4 * sum(self.widths.values())
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def accumulate(self, grads):
+        """grads: dict name -> tensor (any shape with P*width elements); adds one view's gradients."""
+        for k, v in self.views.items():
+            v.add_(grads[k].reshape(v.shape))
+
+    def all_reduce(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return self.flat

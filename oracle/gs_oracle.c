@@ -397,7 +397,10 @@ void gso_render_forward(int W, int H, int F, const uint32_t* ranges, const uint3
 	}
 }
 
-static inline void atomic_addf(float* p, float v)
+/* The reference sums per-pixel contributions with unordered fp32 atomics (backward.cu:541-590), so its own gradients
+ * carry summation-order noise (~1e-4 relative on cancelling sums).  The oracle accumulates the same addends in double
+ * and rounds once, which makes it the better yardstick for both the reference and the CUDA implementation. */
+static inline void atomic_addd(double* p, double v)
 {
 #pragma omp atomic
 	*p += v;
@@ -408,7 +411,7 @@ static inline void atomic_addf(float* p, float v)
  * Outputs (caller-zeroed, rasterize_points.cu:167-184): dL_dmean2D [P,3], dL_dconic [P,4] (slots x,y,w used),
  * dL_dopacity [P], dL_dcolors [P,3], dL_dfeature [P,F].
  */
-void gso_render_backward(int W, int H, int F, const uint32_t* ranges, const uint32_t* point_list,
+void gso_render_backward(int P, int W, int H, int F, const uint32_t* ranges, const uint32_t* point_list,
 	const float* bg_color, const float* means2D, const float* conic_opacity, const float* colors, const float* feature,
 	const float* final_Ts, const uint32_t* n_contrib, const float* dL_dpixels, const float* dL_dpixels_F,
 	float* dL_dmean2D, float* dL_dconic2D, float* dL_dopacity, float* dL_dcolors, float* dL_dfeature)
@@ -416,11 +419,16 @@ void gso_render_backward(int W, int H, int F, const uint32_t* ranges, const uint
 	const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
 	const size_t HW = (size_t)H * W;
 	const float ddelx_dx = (float)(0.5 * W), ddely_dy = (float)(0.5 * H); /* :462-463 */
+	const int nf = F > 0 ? F : 1;
+	double* A_mean2D = (double*)calloc((size_t)P * 3, sizeof(double));
+	double* A_conic = (double*)calloc((size_t)P * 4, sizeof(double));
+	double* A_opac = (double*)calloc((size_t)P, sizeof(double));
+	double* A_col = (double*)calloc((size_t)P * 3, sizeof(double));
+	double* A_feat = (double*)calloc((size_t)P * nf, sizeof(double));
 #pragma omp parallel for schedule(dynamic, 1)
 	for (int tile = 0; tile < gx * gy; tile++) {
 		const int ty = tile / gx, tx = tile % gx;
 		const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
-		const int nf = F > 0 ? F : 1;
 		float* accum_rec_F = (float*)malloc(sizeof(float) * nf * 3);
 		float* last_F = accum_rec_F + nf;
 		float* dpixF = accum_rec_F + 2 * nf;
@@ -457,14 +465,14 @@ void gso_render_backward(int W, int H, int F, const uint32_t* ranges, const uint
 						accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
 						last_color[ch] = c;
 						dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
-						atomic_addf(&dL_dcolors[3 * (size_t)g + ch], dchannel_dcolor * dL_dpixel[ch]);
+						atomic_addd(&A_col[3 * (size_t)g + ch], dchannel_dcolor * dL_dpixel[ch]);
 					}
 					for (int ch = 0; ch < F; ch++) {
 						const float f = feature[(size_t)g * F + ch];
 						accum_rec_F[ch] = last_alpha * last_F[ch] + (1.f - last_alpha) * accum_rec_F[ch];
 						last_F[ch] = f;
 						dL_dalpha += (f - accum_rec_F[ch]) * dpixF[ch];
-						atomic_addf(&dL_dfeature[(size_t)g * F + ch], dchannel_dcolor * dpixF[ch]);
+						atomic_addd(&A_feat[(size_t)g * F + ch], dchannel_dcolor * dpixF[ch]);
 					}
 					dL_dalpha *= T;
 					last_alpha = alpha;
@@ -475,16 +483,21 @@ void gso_render_backward(int W, int H, int F, const uint32_t* ranges, const uint
 					const float gdx = G * dx, gdy = G * dy;
 					const float dG_ddelx = -gdx * co[0] - gdy * co[1];
 					const float dG_ddely = -gdy * co[2] - gdx * co[1];
-					atomic_addf(&dL_dmean2D[3 * (size_t)g + 0], dL_dG * dG_ddelx * ddelx_dx);
-					atomic_addf(&dL_dmean2D[3 * (size_t)g + 1], dL_dG * dG_ddely * ddely_dy);
-					atomic_addf(&dL_dconic2D[4 * (size_t)g + 0], -0.5f * gdx * dx * dL_dG);
-					atomic_addf(&dL_dconic2D[4 * (size_t)g + 1], -0.5f * gdx * dy * dL_dG);
-					atomic_addf(&dL_dconic2D[4 * (size_t)g + 3], -0.5f * gdy * dy * dL_dG);
-					atomic_addf(&dL_dopacity[g], G * dL_dalpha);
+					atomic_addd(&A_mean2D[3 * (size_t)g + 0], dL_dG * dG_ddelx * ddelx_dx);
+					atomic_addd(&A_mean2D[3 * (size_t)g + 1], dL_dG * dG_ddely * ddely_dy);
+					atomic_addd(&A_conic[4 * (size_t)g + 0], -0.5f * gdx * dx * dL_dG);
+					atomic_addd(&A_conic[4 * (size_t)g + 1], -0.5f * gdx * dy * dL_dG);
+					atomic_addd(&A_conic[4 * (size_t)g + 3], -0.5f * gdy * dy * dL_dG);
+					atomic_addd(&A_opac[g], G * dL_dalpha);
 				}
 			}
 		free(accum_rec_F);
 	}
+	for (size_t i = 0; i < (size_t)P * 3; i++) { dL_dmean2D[i] = (float)A_mean2D[i]; dL_dcolors[i] = (float)A_col[i]; }
+	for (size_t i = 0; i < (size_t)P * 4; i++) dL_dconic2D[i] = (float)A_conic[i];
+	for (size_t i = 0; i < (size_t)P; i++) dL_dopacity[i] = (float)A_opac[i];
+	if (F > 0) for (size_t i = 0; i < (size_t)P * F; i++) dL_dfeature[i] = (float)A_feat[i];
+	free(A_mean2D); free(A_conic); free(A_opac); free(A_col); free(A_feat);
 }
 
 /* auxiliary.h:107-117 */

@@ -137,7 +137,7 @@ def backward(fw, dL_dcolor, dL_dfeature, means3D, viewmatrix, projmatrix, campos
         dL_dsh=np.zeros((P, M, 3), np.float32), dL_dscales=np.zeros((P, 3), np.float32),
         dL_drotations=np.zeros((P, 4), np.float32))
     colors = colors_precomp if colors_precomp is not None else fw["rgb"]
-    L.gso_render_backward(C.c_int(W), C.c_int(H), C.c_int(F), _p(fw["ranges"]), _p(fw["point_list"]), _p(bg),
+    L.gso_render_backward(C.c_int(P), C.c_int(W), C.c_int(H), C.c_int(F), _p(fw["ranges"]), _p(fw["point_list"]), _p(bg),
                           _p(fw["means2D"]), _p(fw["conic_opacity"]), _p(colors), _p(feature), _p(fw["final_T"]),
                           _p(fw["n_contrib"]), _p(dL_dcolor), _p(dL_dfeature), _p(g["dL_dmeans2D"]), _p(g["dL_dconic"]),
                           _p(g["dL_dopacity"]), _p(g["dL_dcolors"]), _p(g["dL_dfeature"]))
