@@ -45,7 +45,14 @@ class _Alloc:
         self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
 
         def _cb(_user, nbytes):
-            self.tensor = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
+            # Round large requests up to a geometric bucket (<= 25 % slack): the binning state's size follows the
+            # data-dependent instance count, and near-equal sizes must hit the same cached block or the caching
+            # allocator keeps falling back to cudaMalloc/cudaFree (device-wide syncs) for many iterations.
+            n = max(int(nbytes), 1)
+            if n > (1 << 20):
+                q = 1 << max(20, n.bit_length() - 3)
+                n = (n + q - 1) // q * q
+            self.tensor = torch.empty(n, dtype=torch.uint8, device=self.device)
             return self.tensor.data_ptr()
 
         self.fn = _b.ALLOC_FN(_cb)

@@ -629,7 +629,12 @@ void gso_preprocess_backward(int P, int D, int M, const float* means3D, const in
 		const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
 		mat3 cov2D = m3mul(m3mul(m3t(T), m3t(Vrk)), T);
 		float a = cov2D.m[0][0] + 0.3f, b = cov2D.m[0][1], c = cov2D.m[1][1] + 0.3f;
-		float denom = a * c - b * b;
+		/* backward.cu:201: `denom = a*c - b*b`, and `(denom - a*c)` two lines below, cancel catastrophically when
+		 * b*b << a*c (large, nearly axis-aligned splats), so the result depends on how nvcc contracts them.  The
+		 * sm_100 SASS of this expression is FMUL t=a*c; FFMA denom=fma(-b,b,t); FADD (denom - t) -- restated here
+		 * with fmaf so the oracle reproduces the reference's rounding instead of gcc's uncontracted one. */
+		const float ac = a * c;
+		float denom = fmaf(-b, b, ac);
 		float dL_da = 0, dL_db = 0, dL_dc = 0;
 		float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
 		float* dcov = dL_dcov3D + 6 * (size_t)idx;
@@ -637,8 +642,8 @@ void gso_preprocess_backward(int P, int D, int M, const float* means3D, const in
 #define V_(i, j) Vrk.m[i][j]
 #define W_(i, j) Wm.m[i][j]
 		if (denom2inv != 0) {
-			dL_da = denom2inv * (-c * c * dLc[0] + 2 * b * c * dLc[1] + (denom - a * c) * dLc[2]);
-			dL_dc = denom2inv * (-a * a * dLc[2] + 2 * a * b * dLc[1] + (denom - a * c) * dLc[0]);
+			dL_da = denom2inv * (-c * c * dLc[0] + 2 * b * c * dLc[1] + (denom - ac) * dLc[2]);
+			dL_dc = denom2inv * (-a * a * dLc[2] + 2 * a * b * dLc[1] + (denom - ac) * dLc[0]);
 			dL_db = denom2inv * 2 * (b * c * dLc[0] - (denom + 2 * b * b) * dLc[1] + a * b * dLc[2]);
 			dcov[0] = (T_(0, 0) * T_(0, 0) * dL_da + T_(0, 0) * T_(1, 0) * dL_db + T_(1, 0) * T_(1, 0) * dL_dc);
 			dcov[3] = (T_(0, 1) * T_(0, 1) * dL_da + T_(0, 1) * T_(1, 1) * dL_db + T_(1, 1) * T_(1, 1) * dL_dc);
