@@ -47,43 +47,57 @@ def log(*a):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region.  Uses in-process NVML (initialised before
+    warm-up: spawning nvidia-smi makes NVML initialise concurrently with the timed region, which stalls CUDA driver
+    calls for tens of milliseconds); falls back to an `nvidia-smi -lms` child that is given time to start."""
+    BITS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period=0.1):
+        self.index, self.period, self.rows, self.stop_flag, self.thread, self.h = index, period, [], False, None, None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                        try:
+                            rs = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                        except Exception:
+                            rs = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                        self.rows.append((time.perf_counter(), float(mhz), int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(self.period)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["NVML unavailable"], "samples": 0}
+        rows = [r for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)] or self.rows[-1:]
+        reasons = sorted({n for (_, _, rs) in rows for (n, b) in self.BITS if rs & b})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(rows), "source": "NVML, in-process, %.0f ms period" % (self.period * 1e3)}
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -199,16 +213,38 @@ def make_packed(P, F, M, torch):
     return pk.flat, pk.views
 
 
-def run_step(impl, G, C, T, flat, acc, dist=None):
+def run_step(impl, G, C, T, flat, acc, dist=None, streams=None):
+    """One step: fwd+bwd of every local view, gradients summed into the packed buffer, one all-reduce.
+    With `streams` (ours only: the C ABI takes the caller's stream) independent views are enqueued on different CUDA
+    streams so their kernels overlap; the reference launches on the legacy default stream and cannot."""
+    import torch
     flat.zero_()
     Rs = 0
-    for cam, ct in zip(C, T):
-        out = impl.fwd(G, cam)
-        grads = impl.bwd(G, cam, out, ct)
-        Rs += int(out[0])
-        gd = dict(zip(GRAD_ORDER, grads))
-        for k, v in acc.items():
-            v.add_(gd[k].reshape(v.shape))
+    if not streams:
+        for cam, ct in zip(C, T):
+            out = impl.fwd(G, cam)
+            grads = impl.bwd(G, cam, out, ct)
+            Rs += int(out[0])
+            gd = dict(zip(GRAD_ORDER, grads))
+            for k, v in acc.items():
+                v.add_(gd[k].reshape(v.shape))
+    else:
+        main = torch.cuda.current_stream()
+        for s in streams:
+            s.wait_stream(main)
+        results = []
+        for i, (cam, ct) in enumerate(zip(C, T)):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                out = impl.fwd(G, cam)
+                results.append((out, impl.bwd(G, cam, out, ct)))
+        for s in streams:
+            main.wait_stream(s)
+        for out, grads in results:
+            Rs += int(out[0])
+            gd = dict(zip(GRAD_ORDER, grads))
+            for k, v in acc.items():
+                gd[k].record_stream(main)
+                v.add_(gd[k].reshape(v.shape))
     if dist is not None:
         dist.all_reduce(flat)
     return Rs
@@ -326,12 +362,17 @@ def cpu_baseline(wl, budget_gaussians=100_000):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--settle", type=float, default=1.5, help="seconds of untimed steps before the W warm-up steps "
+                    "(lets clocks/power state and the caching allocator reach steady state)")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the run")
+    ap.add_argument("--no-stage-timing", action="store_true", help="do not bracket stages with CUDA events")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams over which independent views are enqueued (ours only)")
     a = ap.parse_args()
     wl = dict(WORKLOADS[a.workload])
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -376,29 +417,49 @@ def main():
     impl = Impl(F, wl["depth"]) if a.impl == "ours" else RefImpl(F, wl["depth"])
     flat, acc = make_packed(P, F, M, torch)
 
+    streams = None
+    if a.impl == "ours" and a.streams > 1 and V > 1:
+        streams = [torch.cuda.Stream() for _ in range(min(a.streams, V))]
+    cfg["view_streams"] = len(streams) if streams else 1
+
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        Rtot = run_step(impl, G, C, T, flat, acc, dist)
+    sampler = ClockSampler(local_rank)
+    if not a.no_clocks:
+        sampler.start()
+        time.sleep(0.3)
     if a.impl == "ours":
         from manigaussian_b200 import _binding
+        _binding.profile_enable(not a.no_stage_timing)
+    t_settle, n_settle = time.perf_counter(), 0
+    while time.perf_counter() - t_settle < a.settle:
+        Rtot = run_step(impl, G, C, T, flat, acc, dist, streams)
+        torch.cuda.synchronize()
+        n_settle += 1
+    cfg["settle_steps"] = n_settle
+    for _ in range(a.warmup):
+        Rtot = run_step(impl, G, C, T, flat, acc, dist, streams)
+    if a.impl == "ours":
         _binding.profile_read()
-        _binding.profile_enable(True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.perf_counter()
     e0.record()
+    step_marks = []
     for _ in range(a.steps):
-        Rtot = run_step(impl, G, C, T, flat, acc, dist)
+        Rtot = run_step(impl, G, C, T, flat, acc, dist, streams)
+        step_marks.append(time.perf_counter())
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    t_stop = time.perf_counter()
+    cfg["host_step_ms"] = [round((b_ - a_) * 1e3, 2) for a_, b_ in zip([t_start] + step_marks[:-1], step_marks)]
+    clocks = sampler.stop(t_start, t_stop)
     ms = e0.elapsed_time(e1)
+    cfg["wall_ms_per_step"] = (t_stop - t_start) * 1e3 / a.steps
     stages = None
     if a.impl == "ours":
         stages = _binding.profile_read()
@@ -451,6 +512,7 @@ def main():
                pipeline_hbm_gbs=balg_view * V / (ms_step * 1e-3) / 1e9, pipeline_frac_of_peak=balg_view * V / (ms_step * 1e-3) / 1e9 / peak,
                l2="no flush: per-step working set (inputs+state+grads, %.0f MB) exceeds the 126 MB L2" % (
                    (P * (232 + 4 * (27 + F + 3 * M)) + 100 * R_view + 8 * N * (3 + F)) / 1e6))
+    dom = None
     if stages is not None:
         per = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
         cfg["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
@@ -458,6 +520,9 @@ def main():
         out["gpu_launches"] = int(sum(stages[k][1] for k in hand))
         cfg["library_launches_cub"] = "scan + radix sort (CUB) per view, not counted in gpu_launches"
         dom = max(per, key=per.get)
+        if per[dom] <= 0:
+            dom = None
+    if stages is not None and dom is not None:
         Fp = F + (1 if wl["depth"] else 0)
         live = P  # upper bound: every Gaussian's record/channel row touched once
         alg = {
@@ -472,8 +537,9 @@ def main():
                            "traffic": None, "alg_bytes_per_launch": alg, "ms_per_launch": per[dom], "peak_source": peak_src,
                            "note": "blend kernels are FP32-issue bound, not HBM bound (DESIGN.md)"}
     else:
-        out["gpu_launches"] = 0
-        out["roofline"] = {"bound": "hbm", "kernel": "whole pipeline (reference kernels)", "achieved": cfg["pipeline_hbm_gbs"],
+        if stages is None:
+            out["gpu_launches"] = 0
+        out["roofline"] = {"bound": "hbm", "kernel": "whole pipeline", "achieved": cfg["pipeline_hbm_gbs"],
                            "peak": peak, "unit": "GB/s", "frac": cfg["pipeline_frac_of_peak"], "traffic": None, "peak_source": peak_src}
     if e2e is not None:
         out["e2e"] = e2e

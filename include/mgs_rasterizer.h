@@ -147,7 +147,7 @@ int mgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const
  * Test/diagnostic access to the opaque state (used by the parity tests to compare stage by stage with the
  * reference's GeometryState / BinningState / ImageState, rasterizer_impl.h:29-65).  Each call writes the
  * device address of the named array inside the given state buffer; names:
- *   geometry: "depths" f32[P], "means2D" f32[2P], "cov3D" f32[6P], "conic_opacity" f32[4P], "rgb" f32[3P],
+ *   geometry: "depths" f32[P], "means2D" f32[2P], "cov3D" f32[6P], "conic_opacity" f32[4P], "rgbd" f32[4P] {r,g,b,depth},
  *             "tiles_touched" u32[P], "point_offsets" u32[P], "clamped" u8[P] (3 bits), "extent" f32[2P]
  *   binning : "point_list" u32[R], "point_list_keys" u64[R], "point_list_unsorted" u32[R],
  *             "point_list_keys_unsorted" u64[R], "records" 32-byte records [R]

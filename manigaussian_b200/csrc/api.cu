@@ -72,7 +72,7 @@ static void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 128)
 }
 
 struct GeomState {
-	float* depths; uint8_t* clamped; float2* means2D; float* cov3D; float4* conic_opacity; float* rgb;
+	float* depths; uint8_t* clamped; float2* means2D; float* cov3D; float4* conic_opacity; float4* rgbd;
 	float2* extent; uint32_t* tiles_touched; uint32_t* point_offsets; char* scan_temp; size_t scan_bytes;
 	static GeomState carve(char*& chunk, size_t P)
 	{
@@ -82,7 +82,7 @@ struct GeomState {
 		obtain(chunk, g.means2D, P);
 		obtain(chunk, g.cov3D, P * 6);
 		obtain(chunk, g.conic_opacity, P);
-		obtain(chunk, g.rgb, P * 3);
+		obtain(chunk, g.rgbd, P);
 		obtain(chunk, g.extent, P);
 		obtain(chunk, g.tiles_touched, P);
 		obtain(chunk, g.point_offsets, P);
@@ -206,7 +206,7 @@ int mgs_forward(
 	pa.viewmatrix = viewmatrix; pa.projmatrix = projmatrix; pa.cam_pos = cam_pos;
 	pa.W = width; pa.H = height; pa.tan_fovx = tan_fovx; pa.tan_fovy = tan_fovy; pa.focal_x = focal_x; pa.focal_y = focal_y;
 	pa.grid_x = gx; pa.grid_y = gy;
-	pa.radii = radii; pa.means2D = geom.means2D; pa.depths = geom.depths; pa.cov3D = geom.cov3D; pa.rgb = geom.rgb;
+	pa.radii = radii; pa.means2D = geom.means2D; pa.depths = geom.depths; pa.cov3D = geom.cov3D; pa.rgbd = geom.rgbd;
 	pa.conic_opacity = geom.conic_opacity; pa.extent = geom.extent; pa.clamped = geom.clamped; pa.tiles_touched = geom.tiles_touched;
 	{ StageTimer t_(ST_PROJECT_FWD, st); launch_project_fwd(pa, st); }
 	MGS_STAGE("project_fwd");
@@ -242,8 +242,7 @@ int mgs_forward(
 	BlendArgs ba{};
 	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F; ba.nq = nq_for(F);
 	ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
-	ba.rgb = colors_precomp ? colors_precomp : geom.rgb;
-	ba.depths = geom.depths; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
+	ba.rgbd = geom.rgbd; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
 	ba.want_depth = out_depth != nullptr;
 	ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
 	ba.out_color = out_color; ba.out_feature = out_feature; ba.out_depth = out_depth;
@@ -290,8 +289,7 @@ int mgs_backward(
 	BlendArgs ba{};
 	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F; ba.nq = nq_for(F);
 	ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
-	ba.rgb = colors_precomp ? colors_precomp : geom.rgb;
-	ba.depths = geom.depths; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
+	ba.rgbd = geom.rgbd; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
 	ba.want_depth = dL_dpix_depth != nullptr;
 	ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
 	ba.dL_dcolor = dL_dpix; ba.dL_dfeature = F > 0 ? dL_dpix_F : nullptr; ba.dL_ddepth = dL_dpix_depth;
@@ -368,7 +366,7 @@ int mgs_state_array(const char* which_state, const char* name, char* state, int 
 	if (w == "geometry") {
 		GeomState g = GeomState::carve(state, (size_t)a0);
 		if (n == "depths") p = g.depths; else if (n == "means2D") p = g.means2D; else if (n == "cov3D") p = g.cov3D;
-		else if (n == "conic_opacity") p = g.conic_opacity; else if (n == "rgb") p = g.rgb;
+		else if (n == "conic_opacity") p = g.conic_opacity; else if (n == "rgbd") p = g.rgbd;
 		else if (n == "tiles_touched") p = g.tiles_touched; else if (n == "point_offsets") p = g.point_offsets;
 		else if (n == "clamped") p = g.clamped; else if (n == "extent") p = g.extent;
 	} else if (w == "binning") {

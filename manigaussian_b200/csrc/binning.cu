@@ -10,6 +10,7 @@
 // here is hand-written.  After sorting, one pass writes the per-tile [start,end) ranges AND gathers
 // the per-instance 32-byte records into tile order, so the blend kernels can fetch a tile's work
 // list with a single 1-D TMA bulk copy per batch (the reference gathers by index inside the blend).
+#include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include "mgs_common.cuh"
@@ -100,9 +101,11 @@ __global__ void __launch_bounds__(256) ranges_pack_kernel(int R, const uint64_t*
 	const float2 xy = means2D[g];
 	const float4 co = conic_opacity[g];
 	const float2 ex = extent[g];
+	// extents travel as half2, rounded UP so the cull stays conservative (1e30 -> +inf = "never cull")
+	const __half2 eh = __halves2half2(__float2half_ru(ex.x), __float2half_ru(ex.y));
 	float4* dst = reinterpret_cast<float4*>(recs + idx);
 	dst[0] = make_float4(xy.x, xy.y, co.x, co.y);
-	dst[1] = make_float4(co.z, co.w, ex.x, ex.y);
+	dst[1] = make_float4(co.z, co.w, __uint_as_float(*reinterpret_cast<const uint32_t*>(&eh)), __uint_as_float(g));
 }
 
 void launch_ranges_and_pack(int R, int num_tiles, const uint64_t* keys, const uint32_t* point_list,

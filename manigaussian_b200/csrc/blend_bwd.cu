@@ -16,24 +16,23 @@
 // per-pixel sequential dependences (transmittance, S) across the 32 Gaussians of the chunk are resolved
 // with warp prefix scans.  No cross-lane reduction of the 9+F gradients is needed, and each (block,
 // Gaussian) pair costs ceil((12+F)/4) 128-bit red.global.add.v4.f32 instead of 9+F scalar atomics per
-// pixel.  Pixel cotangent rows are read as 128-bit shared-memory broadcasts.
+// pixel.  Pixel cotangent rows are read as 128-bit shared-memory broadcasts; records arrive through the
+// TMA ring of blend_common.cuh; each lane fetches its Gaussian's channel row with 128-bit loads.
 #include "blend_common.cuh"
 
 namespace mgs {
 
-template <int NQ>
+template <int NQ, bool VEC>
 __global__ void __launch_bounds__(BLEND_THREADS, 2) blend_bwd_kernel(BlendArgs a)
 {
 	constexpr int NW = BLEND_THREADS / 32;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	unsigned char* sp = smem_raw;
-	InstRec* s_rec = reinterpret_cast<InstRec*>(sp); sp += BATCH * sizeof(InstRec);
-	float4* s_ch = reinterpret_cast<float4*>(sp); sp += (size_t)BATCH * NQ * sizeof(float4);
+	InstRec* s_rec = reinterpret_cast<InstRec*>(sp); sp += (size_t)RING * BATCH * sizeof(InstRec);
 	float4* s_g = reinterpret_cast<float4*>(sp); sp += (size_t)NW * 32 * NQ * sizeof(float4);   // [warp][pixel][q]
 	float4* s_state = reinterpret_cast<float4*>(sp); sp += (size_t)NW * 32 * sizeof(float4);     // {T, S, n_contrib, Tfinal*bg.g}
-	uint32_t* s_id = reinterpret_cast<uint32_t*>(sp); sp += BATCH * sizeof(uint32_t);
 	uint16_t* s_hit = reinterpret_cast<uint16_t*>(sp); sp += (size_t)NW * BATCH * sizeof(uint16_t);
-	__shared__ __align__(8) uint64_t bar;
+	__shared__ __align__(8) uint64_t s_bar[RING];
 	__shared__ uint32_t s_tile_max;
 
 	const int tile = blockIdx.x;
@@ -46,9 +45,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, 2) blend_bwd_kernel(BlendArgs a
 	const float fbx0 = (float)bx0, fbx1 = (float)(bx0 + WARP_BX - 1), fby0 = (float)by0, fby1 = (float)(by0 + WARP_BY - 1);
 	const size_t HW = (size_t)a.H * a.W;
 	const size_t pix = (size_t)a.W * pyi + pxi;
+	const int F = a.F;
 
-	if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); s_tile_max = 0; }
-	uint32_t phase = 0;
+	RecRing ring;
+	ring.init(s_rec, s_bar, a.recs);
+	if (threadIdx.x == 0) s_tile_max = 0;
 	const uint2 range = a.ranges[tile];
 
 	// ---- per-pixel cotangent rows and carried state (lane == pixel here) ----
@@ -67,8 +68,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, 2) blend_bwd_kernel(BlendArgs a
 			if (a.dL_ddepth) g[3] = a.dL_ddepth[pix];
 			if (NQ > 1 && a.dL_dfeature) {
 #pragma unroll
-				for (int k = 0; k < 4 * (NQ - 1); k++)
-					if (k < a.F) g[4 + k] = a.dL_dfeature[(size_t)k * HW + pix];
+				for (int i = 0; i < 4 * (NQ - 1); i++)
+					if (i < F) g[4 + i] = a.dL_dfeature[(size_t)i * HW + pix];
 			}
 		}
 #pragma unroll
@@ -82,34 +83,39 @@ __global__ void __launch_bounds__(BLEND_THREADS, 2) blend_bwd_kernel(BlendArgs a
 	__syncthreads();  // barrier init + s_tile_max = 0 visible
 	if (lane == 0 && maxc > 0) atomicMax(&s_tile_max, maxc);
 	__syncthreads();
-	const uint32_t tile_max = s_tile_max;
+	const int tile_max = (int)s_tile_max;
 	if (tile_max == 0) return;
 
-	const float4* s_rec4 = reinterpret_cast<const float4*>(s_rec);
 	uint16_t* my_hit = s_hit + warp * BATCH;
 	const float4* wg = s_g + (size_t)warp * 32 * NQ;
 	float4* wstate = s_state + warp * 32;
 	const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
 
-	// Only the first tile_max instances of the tile can have contributed to any pixel.
-	const int64_t first = range.x;
-	for (int64_t hi = first + tile_max; hi > first; hi -= BATCH) {
-		const int64_t lo = (hi - BATCH > first) ? hi - BATCH : first;
-		const int n = (int)(hi - lo);
-		__syncthreads();  // previous batch fully consumed
-		stage_batch<NQ>(a, (uint32_t)lo, n, s_rec, s_id, s_ch, &bar, phase);
+	// Only the first tile_max instances of the tile can have contributed to any pixel.  Batches are walked from
+	// the back: batch k covers list positions [lo_k, lo_k + n_k), lo_k = BATCH * (nb - 1 - k).
+	const int nb = (tile_max + BATCH - 1) / BATCH;
+	auto batch_lo = [&](int k) { return BATCH * (nb - 1 - k); };
+	auto batch_n = [&](int k) { return min(BATCH, tile_max - batch_lo(k)); };
+	if (threadIdx.x == 0) {
+		for (int k = 0; k < min(nb, RING - 1); k++) ring.issue(k, range.x + batch_lo(k), batch_n(k));
+	}
+
+	for (int k = 0; k < nb; k++) {
+		__syncthreads();  // batch k-1 fully consumed: its buffer may be refilled
+		if (threadIdx.x == 0 && k + RING - 1 < nb) {
+			const int kk = k + RING - 1;
+			ring.issue(kk, range.x + batch_lo(kk), batch_n(kk));
+		}
+		const float4* rec4 = ring.wait(k);
 		if (maxc == 0) continue;
+		const int lo = batch_lo(k), n = batch_n(k);
 
 		// ---- cull against this warp's 8x4 block; hit list in back-to-front order ----
 		int nh = 0;
 		for (int c = ((n - 1) >> 5) << 5; c >= 0; c -= 32) {
 			const int j = c + lane;
 			bool hit = false;
-			if (j < n) {
-				const float4 r0 = s_rec4[2 * j], r1 = s_rec4[2 * j + 1];
-				const uint32_t pos = (uint32_t)(lo - first) + (uint32_t)j + 1u;
-				hit = (pos <= maxc) && (r1.z >= 0.f) && (r0.x + r1.z >= fbx0) && (r0.x - r1.z <= fbx1) && (r0.y + r1.w >= fby0) && (r0.y - r1.w <= fby1);
-			}
+			if (j < n) hit = ((uint32_t)(lo + j) < maxc) && rec_hits_block(rec4[2 * j], rec4[2 * j + 1], fbx0, fbx1, fby0, fby1);
 			const uint32_t mask = __ballot_sync(0xffffffffu, hit);
 			if (hit) {
 				const uint32_t above = (lane == 31) ? 0u : (mask >> (lane + 1));
@@ -125,17 +131,34 @@ __global__ void __launch_bounds__(BLEND_THREADS, 2) blend_bwd_kernel(BlendArgs a
 			// ---- lane <- Gaussian: record, channel row, zeroed accumulators ----
 			int jj = 0;
 			if (have) jj = my_hit[k0 + lane];
-			float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, -1.f, -1.f);
+			float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (have) { r0 = rec4[2 * jj]; r1 = rec4[2 * jj + 1]; }
+			const uint32_t id = rec_id(r1);
 			float c[4 * NQ], dch[4 * NQ];
-			if (have) { r0 = s_rec4[2 * jj]; r1 = s_rec4[2 * jj + 1]; }
 #pragma unroll
-			for (int q = 0; q < NQ; q++) {
-				float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (have) v = s_ch[(size_t)jj * NQ + q];
-				c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
-				dch[4 * q] = 0.f; dch[4 * q + 1] = 0.f; dch[4 * q + 2] = 0.f; dch[4 * q + 3] = 0.f;
+			for (int i = 0; i < 4 * NQ; i++) { c[i] = 0.f; dch[i] = 0.f; }
+			if (have) {
+				const float4 v = ldg_nc_v4(a.rgbd + id);
+				c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+				if (NQ > 1) {
+					if (VEC) {
+						const float4* row = reinterpret_cast<const float4*>(a.feature + (size_t)id * F);
+#pragma unroll
+						for (int q = 1; q < NQ; q++) {
+							if (4 * (q - 1) < F) {
+								const float4 u = ldg_nc_v4(row + (q - 1));
+								c[4 * q] = u.x; c[4 * q + 1] = u.y; c[4 * q + 2] = u.z; c[4 * q + 3] = u.w;
+							}
+						}
+					} else {
+						const float* row = a.feature + (size_t)id * F;
+#pragma unroll
+						for (int i = 0; i < 4 * (NQ - 1); i++)
+							if (i < F) c[4 + i] = __ldg(row + i);
+					}
+				}
 			}
-			const uint32_t pos = (uint32_t)(lo - first) + (uint32_t)jj + 1u;
+			const uint32_t pos = (uint32_t)(lo + jj) + 1u;
 			const float gx_ = r0.x, gy_ = r0.y, ca = r0.z, cb = r0.w, cc = r1.x, op = r1.y;
 			float dmx = 0.f, dmy = 0.f, dca = 0.f, dcb = 0.f, dcc = 0.f, dop = 0.f;
 
@@ -201,21 +224,20 @@ __global__ void __launch_bounds__(BLEND_THREADS, 2) blend_bwd_kernel(BlendArgs a
 
 			// ---- flush this Gaussian's gradients: 128-bit reductions to L2 ----
 			if (have) {
-				const uint32_t id = s_id[jj];
 				float* gb = a.gb + (size_t)id * GB_STRIDE;
 				red_add_v4(gb, dmx, dmy, dca, dcb);
 				red_add_v4(gb + 4, dcc, dop, dch[0], dch[1]);
 				red_add_v4(gb + 8, dch[2], dch[3], 0.f, 0.f);
 				if (NQ > 1 && a.dL_dfeat) {
-					float* df = a.dL_dfeat + (size_t)id * a.F;
-					if ((a.F & 3) == 0) {
+					float* df = a.dL_dfeat + (size_t)id * F;
+					if (VEC) {
 #pragma unroll
 						for (int q = 1; q < NQ; q++)
-							if (4 * (q - 1) < a.F) red_add_v4(df + 4 * (q - 1), dch[4 * q], dch[4 * q + 1], dch[4 * q + 2], dch[4 * q + 3]);
+							if (4 * (q - 1) < F) red_add_v4(df + 4 * (q - 1), dch[4 * q], dch[4 * q + 1], dch[4 * q + 2], dch[4 * q + 3]);
 					} else {
 #pragma unroll
-						for (int k = 0; k < 4 * (NQ - 1); k++)
-							if (k < a.F) red_add(df + k, dch[4 + k]);
+						for (int i = 0; i < 4 * (NQ - 1); i++)
+							if (i < F) red_add(df + i, dch[4 + i]);
 					}
 				}
 			}
@@ -223,23 +245,33 @@ __global__ void __launch_bounds__(BLEND_THREADS, 2) blend_bwd_kernel(BlendArgs a
 	}
 }
 
+bool feature_rows_vectorizable(const float* feature, int F);
+
 static size_t bwd_smem_bytes(int nq)
 {
 	constexpr int NW = BLEND_THREADS / 32;
-	return BATCH * sizeof(InstRec) + (size_t)BATCH * nq * sizeof(float4) + (size_t)NW * 32 * nq * sizeof(float4) +
-		(size_t)NW * 32 * sizeof(float4) + BATCH * sizeof(uint32_t) + (size_t)NW * BATCH * sizeof(uint16_t);
+	return (size_t)RING * BATCH * sizeof(InstRec) + (size_t)NW * 32 * nq * sizeof(float4) + (size_t)NW * 32 * sizeof(float4) +
+		(size_t)NW * BATCH * sizeof(uint16_t);
+}
+
+template <int NQ, bool VEC>
+static void launch_bwd_tv(const BlendArgs& a, cudaStream_t s)
+{
+	const size_t smem = bwd_smem_bytes(NQ);
+	static bool configured = false;
+	if (!configured) {
+		cudaFuncSetAttribute(blend_bwd_kernel<NQ, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		configured = true;
+	}
+	blend_bwd_kernel<NQ, VEC><<<a.grid_x * a.grid_y, BLEND_THREADS, smem, s>>>(a);
 }
 
 template <int NQ>
 static void launch_bwd_t(const BlendArgs& a, cudaStream_t s)
 {
-	const size_t smem = bwd_smem_bytes(NQ);
-	static bool configured = false;
-	if (!configured) {
-		cudaFuncSetAttribute(blend_bwd_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		configured = true;
-	}
-	blend_bwd_kernel<NQ><<<a.grid_x * a.grid_y, BLEND_THREADS, smem, s>>>(a);
+	const bool vec = NQ == 1 || (feature_rows_vectorizable(a.feature, a.F) && (reinterpret_cast<uintptr_t>(a.dL_dfeat) & 15) == 0);
+	if (vec) launch_bwd_tv<NQ, true>(a, s);
+	else launch_bwd_tv<NQ, false>(a, s);
 }
 
 void launch_blend_bwd(const BlendArgs& a, cudaStream_t s)

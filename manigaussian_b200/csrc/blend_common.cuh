@@ -1,59 +1,66 @@
-// Staging shared by the forward and backward blend kernels: one batch of a tile's sorted work list is
-// brought into shared memory as
-//   s_rec[j]  : 32-byte InstRec, ONE contiguous TMA bulk copy for the whole batch (UBLKCP)
-//   s_id[j]   : Gaussian id
-//   s_ch[j][q]: channel row {r, g, b, depth | f0..f3 | ...}, NQ float4s; the feature part is one TMA
-//               bulk copy per row (rows are 16-byte multiples when F % 4 == 0), rgb/depth by plain loads.
-// Completion of all bulk copies of a batch is tracked by a single mbarrier (expect_tx = total bytes).
+// Shared by the forward and backward blend kernels: a 3-deep ring of shared-memory buffers into which one
+// elected thread streams a tile's sorted 32-byte instance records with 1-D TMA bulk copies (UBLKCP), one
+// copy per batch of up to BATCH records, completion tracked by one mbarrier per buffer.  Records of batch
+// k+2 are in flight while batch k is consumed, so the only per-batch synchronisation is the CTA barrier that
+// retires batch k-1's buffer.
+//
+// Channel rows ({r,g,b,depth} float4 + F feature floats per Gaussian) are NOT staged: they are read from
+// global memory with 128-bit loads through the read-only path -- warp-uniform addresses in the forward
+// (one transaction per load, L1-resident across the 8 warps of a tile), per-lane rows in the backward.
 #pragma once
+#include <cuda_fp16.h>
 #include "mgs_common.cuh"
 #include "mgs_kernels.h"
 
 namespace mgs {
 
 constexpr int BLEND_THREADS = 256;
-constexpr int BATCH = 256;  // instances staged per round (one per thread)
+constexpr int BATCH = 256;  // records per bulk copy (8 KB)
+constexpr int RING = 3;
 
-// Stage instances [lo, lo+n) of the sorted list.  Must be called by all BLEND_THREADS threads, after a
-// __syncthreads() that retired every read of the previous batch.  Returns after the data is visible.
-template <int NQ>
-__device__ __forceinline__ void stage_batch(const BlendArgs& a, uint32_t lo, int n, InstRec* s_rec, uint32_t* s_id,
-	float4* s_ch, uint64_t* bar, uint32_t& phase)
-{
-	const int t = threadIdx.x;
-	const int F = a.F;
-	const bool bulk_feat = (F > 0) && ((F & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.feature) & 15) == 0);
-	if (t == 0) {
-		fence_proxy_async();
-		uint32_t bytes = (uint32_t)n * (uint32_t)sizeof(InstRec);
-		if (bulk_feat) bytes += (uint32_t)n * (uint32_t)F * 4u;
-		mbar_arrive_expect_tx(bar, bytes);
-		bulk_g2s(s_rec, a.recs + lo, (uint32_t)n * (uint32_t)sizeof(InstRec), bar);
-	}
-	if (t < n) {
-		const uint32_t id = a.point_list[lo + t];
-		s_id[t] = id;
-		float4* row = s_ch + (size_t)t * NQ;
-		const float* c = a.rgb + 3 * (size_t)id;
-		row[0] = make_float4(c[0], c[1], c[2], a.want_depth ? a.depths[id] : 0.f);
-		if (NQ > 1) {
-			if (bulk_feat) {
-				bulk_g2s(row + 1, a.feature + (size_t)id * F, (uint32_t)F * 4u, bar);
-				// zero the padding quads beyond F (only when 4 + F is not a multiple covered by NQ)
+struct RecRing {
+	InstRec* buf;      // RING * BATCH records
+	uint64_t* bar;     // RING mbarriers
+	const InstRec* src;
+
+	__device__ __forceinline__ void init(InstRec* b, uint64_t* bars, const InstRec* s)
+	{
+		buf = b; bar = bars; src = s;
+		if (threadIdx.x == 0) {
 #pragma unroll
-				for (int q = 1; q < NQ; q++)
-					if (4 * (q - 1) >= F) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-			} else {
-				float* rf = reinterpret_cast<float*>(row + 1);
-				const float* f = a.feature ? a.feature + (size_t)id * F : nullptr;
-#pragma unroll
-				for (int k = 0; k < 4 * (NQ - 1); k++) rf[k] = (k < F) ? f[k] : 0.f;
-			}
+			for (int i = 0; i < RING; i++) mbar_init(&bar[i], 1);
+			mbar_fence_init();
 		}
 	}
-	__syncthreads();          // plain stores visible to the CTA
-	mbar_wait(bar, phase);    // bulk copies landed
-	phase ^= 1;
+	// thread 0 only: start the copy of records [lo, lo+n) into buffer k % RING
+	__device__ __forceinline__ void issue(int k, uint32_t lo, int n)
+	{
+		const int b = k % RING;
+		fence_proxy_async();
+		mbar_arrive_expect_tx(&bar[b], (uint32_t)n * (uint32_t)sizeof(InstRec));
+		bulk_g2s(buf + b * BATCH, src + lo, (uint32_t)n * (uint32_t)sizeof(InstRec), &bar[b]);
+	}
+	// all threads: wait until batch k has landed; returns its buffer
+	__device__ __forceinline__ const float4* wait(int k)
+	{
+		const int b = k % RING;
+		mbar_wait(&bar[b], (uint32_t)((k / RING) & 1));
+		return reinterpret_cast<const float4*>(buf + b * BATCH);
+	}
+};
+
+// {x, y, ca, cb} and {cc, op, ext(half2 hx,hy), id} views of a record
+__device__ __forceinline__ float2 rec_extent(const float4& r1)
+{
+	return __half22float2(*reinterpret_cast<const __half2*>(&r1.z));
+}
+__device__ __forceinline__ uint32_t rec_id(const float4& r1) { return __float_as_uint(r1.w); }
+
+// does the alpha >= 1/255 footprint of the record overlap the pixel block [x0,x1] x [y0,y1]?
+__device__ __forceinline__ bool rec_hits_block(const float4& r0, const float4& r1, float x0, float x1, float y0, float y1)
+{
+	const float2 e = rec_extent(r1);
+	return (e.x >= 0.f) && (r0.x + e.x >= x0) && (r0.x - e.x <= x1) && (r0.y + e.y >= y0) && (r0.y - e.y <= y1);
 }
 
 }  // namespace mgs

@@ -27,7 +27,9 @@ struct __align__(16) InstRec {
 	float x, y;        // pixel-space mean (geom means2D)
 	float ca, cb;      // conic.x, conic.y
 	float cc, op;      // conic.z, opacity
-	float hx, hy;      // conservative half-extent of the alpha >= 1/255 footprint (cull only)
+	uint32_t ext;      // half2 {hx, hy}: conservative (rounded up) half-extent of the alpha >= 1/255 footprint;
+	                   // -1 = never contributes, +inf = unknown (never cull).  Cull only, never changes a pixel.
+	uint32_t id;       // Gaussian index (== point_list entry)
 };
 static_assert(sizeof(InstRec) == 32, "InstRec must be 32 bytes");
 

@@ -29,7 +29,7 @@ struct ProjectFwdArgs {
 	float2* means2D;
 	float* depths;
 	float* cov3D;
-	float* rgb;
+	float4* rgbd;  // {r, g, b, view-space depth} per Gaussian: the first quad of the blend channel row
 	float4* conic_opacity;
 	float2* extent;
 	uint8_t* clamped;  // 3 bits per Gaussian
@@ -73,8 +73,7 @@ struct BlendArgs {
 	const uint2* ranges;         // [T]
 	const uint32_t* point_list;  // [R] sorted Gaussian ids
 	const InstRec* recs;         // [R] sorted packed records
-	const float* rgb;            // [P,3]
-	const float* depths;         // [P]
+	const float4* rgbd;          // [P] {r,g,b,depth}
 	const float* feature;        // [P,F] or null
 	const float* bg;             // [3]
 	int want_depth;

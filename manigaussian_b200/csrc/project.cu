@@ -152,13 +152,13 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjectFwdArgs a)
 	tile_rect(px, py, (int)my_radius, rmin, rmax, a.grid_x, a.grid_y);
 	if ((rmax.x - rmin.x) * (rmax.y - rmin.y) == 0) return;
 
+	float c[3];
 	if (a.colors_precomp == nullptr) {
-		float c[3];
 		sh_to_rgb(idx, a.D, a.M, a.means3D, a.cam_pos, a.shs, a.clamped, c);
-		a.rgb[3 * idx + 0] = c[0];
-		a.rgb[3 * idx + 1] = c[1];
-		a.rgb[3 * idx + 2] = c[2];
+	} else {
+		c[0] = a.colors_precomp[3 * idx]; c[1] = a.colors_precomp[3 * idx + 1]; c[2] = a.colors_precomp[3 * idx + 2];
 	}
+	a.rgbd[idx] = make_float4(c[0], c[1], c[2], p_view.z);  // blend channel quad 0 (depth rides as a channel)
 
 	const float opacity = a.opacities[idx];
 	out_radius = (int)my_radius;

@@ -38,24 +38,42 @@ def _prep(t, device):
 
 
 class _Alloc:
-    """Allocator callback backed by torch's caching allocator (replaces resizeFunctional, rasterize_points.cu:27-33)."""
+    """State-buffer allocation backed by torch's caching allocator (replaces resizeFunctional, rasterize_points.cu:27-33).
+    One process-wide C callback serves every call; the `user` pointer selects the _Alloc instance."""
+    _live = {}
+    _next = [1]
 
     def __init__(self, device):
         self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.tensor = None
+        self.key = _Alloc._next[0]
+        _Alloc._next[0] += 1
+        _Alloc._live[self.key] = self
 
-        def _cb(_user, nbytes):
-            # Round large requests up to a geometric bucket (<= 25 % slack): the binning state's size follows the
-            # data-dependent instance count, and near-equal sizes must hit the same cached block or the caching
-            # allocator keeps falling back to cudaMalloc/cudaFree (device-wide syncs) for many iterations.
-            n = max(int(nbytes), 1)
-            if n > (1 << 20):
-                q = 1 << max(20, n.bit_length() - 3)
-                n = (n + q - 1) // q * q
-            self.tensor = torch.empty(n, dtype=torch.uint8, device=self.device)
-            return self.tensor.data_ptr()
+    def release(self):
+        _Alloc._live.pop(self.key, None)
+        if self.tensor is None:
+            self.tensor = torch.empty(0, dtype=torch.uint8, device=self.device)
+        return self.tensor
 
-        self.fn = _b.ALLOC_FN(_cb)
+    def alloc(self, nbytes):
+        # Round large requests up to a geometric bucket (<= 25 % slack): the binning state's size follows the
+        # data-dependent instance count, and near-equal sizes must hit the same cached block or the caching
+        # allocator keeps falling back to cudaMalloc for many iterations.
+        n = max(int(nbytes), 1)
+        if n > (1 << 20):
+            q = 1 << max(20, n.bit_length() - 3)
+            n = (n + q - 1) // q * q
+        self.tensor = torch.empty(n, dtype=torch.uint8, device=self.device)
+        return self.tensor.data_ptr()
+
+
+def _alloc_trampoline(user, nbytes):
+    a = _Alloc._live.get(int(user or 0))
+    return a.alloc(nbytes) if a is not None else 0
+
+
+_ALLOC_CB = _b.ALLOC_FN(_alloc_trampoline)
 
 
 def _stream(device):
@@ -94,7 +112,7 @@ def rasterize_gaussians_raw(bg, means3D, colors, language_feature, opacity, scal
     if P != 0:
         with torch.cuda.device(dev):
             rendered = _b.check(L.mgs_forward(
-                ga.fn, None, ba.fn, None, ia.fn, None,
+                _ALLOC_CB, ga.key, _ALLOC_CB, ba.key, _ALLOC_CB, ia.key,
                 P, int(degree), M, F,
                 _ptr(bg), W, H,
                 _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(language_feature) if F else None,
@@ -109,7 +127,7 @@ def rasterize_gaussians_raw(bg, means3D, colors, language_feature, opacity, scal
             out_feature.zero_()
         if out_depth is not None:
             out_depth.zero_()
-    ret = (rendered, out_color, out_feature, radii, ga.tensor, ba.tensor, ia.tensor)
+    ret = (rendered, out_color, out_feature, radii, ga.release(), ba.release(), ia.release())
     return ret + (out_depth,) if return_depth else ret
 
 

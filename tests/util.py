@@ -155,14 +155,14 @@ def run_ours(inp, backward=True, debug=False):
     fw = dict(P=P, W=W, H=H, F=F, M=0 if g["shs"] is None else g["shs"].shape[1], num_rendered=num_rendered,
               out_color=color.cpu().numpy(), out_feature=feature.cpu().numpy(), radii=radii.cpu().numpy())
     for name, dt, cnt in (("depths", torch.float32, P), ("means2D", torch.float32, 2 * P), ("cov3D", torch.float32, 6 * P),
-                          ("conic_opacity", torch.float32, 4 * P), ("rgb", torch.float32, 3 * P),
+                          ("conic_opacity", torch.float32, 4 * P), ("rgbd", torch.float32, 4 * P),
                           ("tiles_touched", torch.int32, P), ("point_offsets", torch.int32, P), ("clamped", torch.uint8, P),
                           ("extent", torch.float32, 2 * P)):
         fw[name] = arr("geometry", name, geomB, P, 0, dt, cnt)
     fw["means2D"] = fw["means2D"].reshape(P, 2)
     fw["cov3D"] = fw["cov3D"].reshape(P, 6)
     fw["conic_opacity"] = fw["conic_opacity"].reshape(P, 4)
-    fw["rgb"] = fw["rgb"].reshape(P, 3)
+    fw["rgb"] = np.ascontiguousarray(fw["rgbd"].reshape(P, 4)[:, :3])
     fw["tiles_touched"] = fw["tiles_touched"].astype(np.uint32)
     Rn = num_rendered
     fw["point_list"] = arr("binning", "point_list", binB, Rn, 0, torch.int32, Rn).astype(np.uint32)

@@ -43,6 +43,17 @@ def seg():
 
 for _ in range(2):
     print(impl_name, wlname, {k: round(v * 1e3, 3) for k, v in seg().items()}, "ms per step (synchronised segments)")
+ms0 = torch.cuda.memory_stats()
+per = []
+for _ in range(30):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    bench.run_step(impl, G, C, T, flat, acc)
+    torch.cuda.synchronize(); per.append(round((time.perf_counter() - t0) * 1e3, 2))
+ms1 = torch.cuda.memory_stats()
+print("30 consecutive steps (ms):", per)
+print("cudaMalloc calls during them:", ms1.get("num_device_alloc", 0) - ms0.get("num_device_alloc", 0),
+      "cudaFree:", ms1.get("num_device_free", 0) - ms0.get("num_device_free", 0),
+      "reserved MB:", ms1["reserved_bytes.all.current"] / 1e6, "allocated MB:", ms1["allocated_bytes.all.current"] / 1e6)
 # host-only cost: how long does the Python/driver side take when the GPU is not waited for
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(5):
