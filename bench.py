@@ -516,9 +516,9 @@ def main():
     if stages is not None:
         per = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
         cfg["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
-        hand = ("project_fwd", "emit_keys", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd")
-        out["gpu_launches"] = int(sum(stages[k][1] for k in hand))
-        cfg["library_launches_cub"] = "scan + radix sort (CUB) per view, not counted in gpu_launches"
+        hand = ("project_fwd", "emit_tiles", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd")
+        out["gpu_launches"] = int(sum(stages[k][1] for k in hand if k in stages))
+        cfg["library_launches_cub"] = "depth sort + scan + tile sort (CUB) per view, not counted in gpu_launches"
         dom = max(per, key=per.get)
         if per[dom] <= 0:
             dom = None
@@ -530,8 +530,9 @@ def main():
             "blend_fwd": 4 * R_view + live * (32 + 4 * (3 + Fp)) + N * (4 * (3 + Fp) + 8),
             "project_fwd": P * (44 + 12 * M + 4 + 32 + 4),
             "project_bwd": P * (44 + 12 * M + 48 + 56 + 12 * M),
-            "sort": 2 * 12 * R_view, "emit_keys": P * 20 + 12 * R_view, "ranges_pack": R_view * (12 + 32) + 32 * R_view, "scan": 8 * P,
-        }[dom]
+            "depth_sort": 2 * 8 * P, "tile_sort": 2 * 8 * R_view, "emit_tiles": P * 20 + 8 * R_view,
+            "ranges_pack": R_view * (8 + 32) + 32 * R_view, "scan": 8 * P,
+        }.get(dom, 0)
         ach = alg / (per[dom] * 1e-3) / 1e9
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                            "traffic": None, "alg_bytes_per_launch": alg, "ms_per_launch": per[dom], "peak_source": peak_src,

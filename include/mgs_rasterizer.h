@@ -148,9 +148,11 @@ int mgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const
  * reference's GeometryState / BinningState / ImageState, rasterizer_impl.h:29-65).  Each call writes the
  * device address of the named array inside the given state buffer; names:
  *   geometry: "depths" f32[P], "means2D" f32[2P], "cov3D" f32[6P], "conic_opacity" f32[4P], "rgbd" f32[4P] {r,g,b,depth},
- *             "tiles_touched" u32[P], "point_offsets" u32[P], "clamped" u8[P] (3 bits), "extent" f32[2P]
- *   binning : "point_list" u32[R], "point_list_keys" u64[R], "point_list_unsorted" u32[R],
- *             "point_list_keys_unsorted" u64[R], "records" 32-byte records [R]
+ *             "tiles_touched" u32[P], "point_offsets" u32[P] (inclusive sum in depth order), "depth_order" u32[P],
+ *             "clamped" u8[P] (3 bits), "extent" f32[2P]
+ *   binning : "point_list" u32[R] (== the reference's point_list), "tile_ids" u32[R] (== high word of the reference's
+ *             sorted keys; the low word is the depth bits of point_list[i]), "point_list_unsorted" u32[R],
+ *             "tile_ids_unsorted" u32[R], "records" 32-byte records [R]
  *   image   : "final_T" f32[N], "n_contrib" u32[N], "ranges" u32[2T]
  * Returns 0, or MGS_ERR_INVALID_ARG for an unknown name.
  */

@@ -5,6 +5,8 @@
 // every argument follow the reference; the state-buffer layout, kernels and stream handling are ours.
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -40,7 +42,7 @@ static int fail(int code, const std::string& msg)
 	} while (0)
 
 // ---- optional per-stage CUDA-event timing (bench.py's roofline leg); off by default, zero cost when off ----
-enum Stage { ST_PROJECT_FWD = 0, ST_SCAN, ST_EMIT, ST_SORT, ST_RANGES_PACK, ST_BLEND_FWD, ST_BLEND_BWD, ST_PROJECT_BWD, ST_COUNT };
+enum Stage { ST_PROJECT_FWD = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_SORT, ST_RANGES_PACK, ST_BLEND_FWD, ST_BLEND_BWD, ST_PROJECT_BWD, ST_COUNT };
 struct StageEvt { int stage; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
@@ -71,9 +73,27 @@ static void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 128)
 	chunk = reinterpret_cast<char*>(ptr + count);
 }
 
+// CUB temp-storage sizes depend only on the item count; the queries are not free (device attribute lookups), so cache them
+// (sizes are taken for the item count rounded up to a power of two: monotone in n, few distinct keys)
+static size_t cached_temp_bytes(int which, int n)
+{
+	static std::mutex mu;
+	static std::map<std::pair<int, int>, size_t> cache;
+	int nb = 1024;
+	while (nb < n && nb < (1 << 30)) nb <<= 1;
+	std::lock_guard<std::mutex> lk(mu);
+	auto key = std::make_pair(which, nb);
+	auto it = cache.find(key);
+	if (it != cache.end()) return it->second;
+	const size_t bytes = which == 0 ? std::max(scan_temp_bytes(nb), depth_sort_temp_bytes(nb)) : tile_sort_temp_bytes(nb);
+	cache[key] = bytes;
+	return bytes;
+}
+
 struct GeomState {
 	float* depths; uint8_t* clamped; float2* means2D; float* cov3D; float4* conic_opacity; float4* rgbd;
-	float2* extent; uint32_t* tiles_touched; uint32_t* point_offsets; char* scan_temp; size_t scan_bytes;
+	float2* extent; uint32_t* tiles_touched; uint32_t* point_offsets; uint32_t* iota; uint32_t* order; uint32_t* depth_sorted;
+	char* temp; size_t temp_bytes;
 	static GeomState carve(char*& chunk, size_t P)
 	{
 		GeomState g;
@@ -85,9 +105,12 @@ struct GeomState {
 		obtain(chunk, g.rgbd, P);
 		obtain(chunk, g.extent, P);
 		obtain(chunk, g.tiles_touched, P);
-		obtain(chunk, g.point_offsets, P);
-		g.scan_bytes = scan_temp_bytes((int)P);
-		obtain(chunk, g.scan_temp, g.scan_bytes);
+		obtain(chunk, g.point_offsets, P);  // inclusive sum of tiles_touched in DEPTH order
+		obtain(chunk, g.iota, P);
+		obtain(chunk, g.order, P);          // Gaussian ids sorted by depth bits (stable)
+		obtain(chunk, g.depth_sorted, P);
+		g.temp_bytes = cached_temp_bytes(0, (int)P);
+		obtain(chunk, g.temp, g.temp_bytes);
 		return g;
 	}
 };
@@ -103,18 +126,18 @@ struct ImageState {
 	}
 };
 struct BinState {
-	uint32_t* point_list; uint32_t* point_list_unsorted; uint64_t* keys; uint64_t* keys_unsorted; InstRec* recs;
+	uint32_t* point_list; uint32_t* point_list_unsorted; uint32_t* tile_keys; uint32_t* tile_keys_unsorted; InstRec* recs;
 	char* sort_temp; size_t sort_bytes;
 	static BinState carve(char*& chunk, size_t R)
 	{
 		BinState b;
-		const size_t Rp = R + 8;  // slack so bulk copies of the last batch never run past the allocation
-		obtain(chunk, b.point_list, Rp);
-		obtain(chunk, b.point_list_unsorted, Rp);
-		obtain(chunk, b.keys, Rp);
-		obtain(chunk, b.keys_unsorted, Rp);
+		const size_t Rp = R + 8;
+		obtain(chunk, b.point_list, Rp);           // Gaussian ids in (tile, depth) order == the reference's point_list
+		obtain(chunk, b.point_list_unsorted, Rp);  // ... in depth order, before the stable per-tile pass
+		obtain(chunk, b.tile_keys, Rp);            // tile id of every sorted instance (high word of the reference's keys)
+		obtain(chunk, b.tile_keys_unsorted, Rp);
 		obtain(chunk, b.recs, Rp);
-		b.sort_bytes = sort_temp_bytes((int)R);
+		b.sort_bytes = cached_temp_bytes(1, (int)R);
 		obtain(chunk, b.sort_temp, b.sort_bytes);
 		return b;
 	}
@@ -208,10 +231,18 @@ int mgs_forward(
 	pa.grid_x = gx; pa.grid_y = gy;
 	pa.radii = radii; pa.means2D = geom.means2D; pa.depths = geom.depths; pa.cov3D = geom.cov3D; pa.rgbd = geom.rgbd;
 	pa.conic_opacity = geom.conic_opacity; pa.extent = geom.extent; pa.clamped = geom.clamped; pa.tiles_touched = geom.tiles_touched;
+	pa.iota = geom.iota;
 	{ StageTimer t_(ST_PROJECT_FWD, st); launch_project_fwd(pa, st); }
 	MGS_STAGE("project_fwd");
 
-	{ StageTimer t_(ST_SCAN, st); launch_scan(geom.scan_temp, geom.scan_bytes, geom.tiles_touched, geom.point_offsets, P, st); }
+	// Gaussians in depth order (stable: ascending id among equal depth bits; culled ones carry +inf and emit nothing)
+	{
+		StageTimer t_(ST_DEPTH_SORT, st);
+		launch_depth_sort(geom.temp, geom.temp_bytes, reinterpret_cast<const uint32_t*>(geom.depths), geom.depth_sorted, geom.iota,
+			geom.order, P, st);
+	}
+	MGS_STAGE("depth_sort");
+	{ StageTimer t_(ST_SCAN, st); launch_scan_sorted(geom.temp, geom.temp_bytes, geom.order, geom.tiles_touched, geom.point_offsets, P, st); }
 	MGS_STAGE("scan");
 
 	int num_rendered = 0;
@@ -223,18 +254,22 @@ int mgs_forward(
 	if (!bchunk) return fail(MGS_ERR_ALLOC, "binning state allocation failed");
 	BinState bin = BinState::carve(bchunk, (size_t)num_rendered);
 
-	{ StageTimer t_(ST_EMIT, st); launch_emit_keys(P, geom.means2D, geom.depths, geom.point_offsets, radii, gx, gy, bin.keys_unsorted, bin.point_list_unsorted, st); }
-	MGS_STAGE("emit_keys");
+	{
+		StageTimer t_(ST_EMIT, st);
+		launch_emit_tiles(P, geom.order, geom.means2D, geom.point_offsets, radii, gx, gy, bin.tile_keys_unsorted, bin.point_list_unsorted, st);
+	}
+	MGS_STAGE("emit_tiles");
 	if (num_rendered > 0) {
-		const int bit = higher_msb((uint32_t)T);
+		// stable pass(es) over the tile-id bits only: instances already arrive in depth order
+		const int bit = T > 1 ? higher_msb((uint32_t)(T - 1)) : 1;
 		StageTimer t_(ST_SORT, st);
-		launch_sort_pairs(bin.sort_temp, bin.sort_bytes, bin.keys_unsorted, bin.keys, bin.point_list_unsorted, bin.point_list,
-			num_rendered, 32 + bit, st);
-		MGS_STAGE("sort");
+		launch_tile_sort(bin.sort_temp, bin.sort_bytes, bin.tile_keys_unsorted, bin.tile_keys, bin.point_list_unsorted, bin.point_list,
+			num_rendered, bit, st);
+		MGS_STAGE("tile_sort");
 	}
 	{
 		StageTimer t_(ST_RANGES_PACK, st);
-		launch_ranges_and_pack(num_rendered, (int)T, bin.keys, bin.point_list, geom.means2D, geom.conic_opacity, geom.extent,
+		launch_ranges_and_pack(num_rendered, (int)T, bin.tile_keys, bin.point_list, geom.means2D, geom.conic_opacity, geom.extent,
 			img.ranges, bin.recs, st);
 	}
 	MGS_STAGE("ranges_pack");
@@ -341,7 +376,7 @@ int mgs_profile_enable(int on)
 int mgs_profile_num_stages(void) { return ST_COUNT; }
 const char* mgs_profile_stage_name(int i)
 {
-	static const char* names[ST_COUNT] = { "project_fwd", "scan", "emit_keys", "sort", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd" };
+	static const char* names[ST_COUNT] = { "project_fwd", "depth_sort", "scan", "emit_tiles", "tile_sort", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd" };
 	return (i >= 0 && i < ST_COUNT) ? names[i] : "";
 }
 int mgs_profile_read(float* total_ms, int* counts)
@@ -368,11 +403,12 @@ int mgs_state_array(const char* which_state, const char* name, char* state, int 
 		if (n == "depths") p = g.depths; else if (n == "means2D") p = g.means2D; else if (n == "cov3D") p = g.cov3D;
 		else if (n == "conic_opacity") p = g.conic_opacity; else if (n == "rgbd") p = g.rgbd;
 		else if (n == "tiles_touched") p = g.tiles_touched; else if (n == "point_offsets") p = g.point_offsets;
+		else if (n == "depth_order") p = g.order;
 		else if (n == "clamped") p = g.clamped; else if (n == "extent") p = g.extent;
 	} else if (w == "binning") {
 		BinState b = BinState::carve(state, (size_t)a0);
-		if (n == "point_list") p = b.point_list; else if (n == "point_list_keys") p = b.keys;
-		else if (n == "point_list_unsorted") p = b.point_list_unsorted; else if (n == "point_list_keys_unsorted") p = b.keys_unsorted;
+		if (n == "point_list") p = b.point_list; else if (n == "tile_ids") p = b.tile_keys;
+		else if (n == "point_list_unsorted") p = b.point_list_unsorted; else if (n == "tile_ids_unsorted") p = b.tile_keys_unsorted;
 		else if (n == "records") p = b.recs;
 	} else if (w == "image") {
 		ImageState s = ImageState::carve(state, (size_t)a0 * a1, num_tiles(a0, a1));

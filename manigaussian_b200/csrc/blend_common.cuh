@@ -1,12 +1,11 @@
-// Shared by the forward and backward blend kernels: a 3-deep ring of shared-memory buffers into which one
-// elected thread streams a tile's sorted 32-byte instance records with 1-D TMA bulk copies (UBLKCP), one
-// copy per batch of up to BATCH records, completion tracked by one mbarrier per buffer.  Records of batch
-// k+2 are in flight while batch k is consumed, so the only per-batch synchronisation is the CTA barrier that
-// retires batch k-1's buffer.
+// Shared by the forward and backward blend kernels.
 //
-// Channel rows ({r,g,b,depth} float4 + F feature floats per Gaussian) are NOT staged: they are read from
-// global memory with 128-bit loads through the read-only path -- warp-uniform addresses in the forward
-// (one transaction per load, L1-resident across the 8 warps of a tile), per-lane rows in the backward.
+// Work decomposition: ONE WARP = ONE CTA = one 8x4 pixel block of a 16x16 tile (tile ids / work lists stay the
+// reference's 16x16 tiles; eight single-warp CTAs share a tile's list).  A warp streams the tile's sorted 32-byte
+// instance records through its own 3-deep shared-memory ring with 1-D TMA bulk copies (SASS UBLKCP), one copy per
+// batch of REC_BATCH records tracked by an mbarrier, culls each 32-record chunk against its pixel block, and works
+// on the survivors.  No CTA-wide barrier exists anywhere: warps of a heavy tile never wait for each other, finished
+// warps free their SM slot immediately, and the hardware scheduler balances the 8*T*V small CTAs across the 148 SMs.
 #pragma once
 #include <cuda_fp16.h>
 #include "mgs_common.cuh"
@@ -14,40 +13,8 @@
 
 namespace mgs {
 
-constexpr int BLEND_THREADS = 256;
-constexpr int BATCH = 256;  // records per bulk copy (8 KB)
+constexpr int REC_BATCH = 64;  // records per bulk copy (2 KB) = two 32-record chunks
 constexpr int RING = 3;
-
-struct RecRing {
-	InstRec* buf;      // RING * BATCH records
-	uint64_t* bar;     // RING mbarriers
-	const InstRec* src;
-
-	__device__ __forceinline__ void init(InstRec* b, uint64_t* bars, const InstRec* s)
-	{
-		buf = b; bar = bars; src = s;
-		if (threadIdx.x == 0) {
-#pragma unroll
-			for (int i = 0; i < RING; i++) mbar_init(&bar[i], 1);
-			mbar_fence_init();
-		}
-	}
-	// thread 0 only: start the copy of records [lo, lo+n) into buffer k % RING
-	__device__ __forceinline__ void issue(int k, uint32_t lo, int n)
-	{
-		const int b = k % RING;
-		fence_proxy_async();
-		mbar_arrive_expect_tx(&bar[b], (uint32_t)n * (uint32_t)sizeof(InstRec));
-		bulk_g2s(buf + b * BATCH, src + lo, (uint32_t)n * (uint32_t)sizeof(InstRec), &bar[b]);
-	}
-	// all threads: wait until batch k has landed; returns its buffer
-	__device__ __forceinline__ const float4* wait(int k)
-	{
-		const int b = k % RING;
-		mbar_wait(&bar[b], (uint32_t)((k / RING) & 1));
-		return reinterpret_cast<const float4*>(buf + b * BATCH);
-	}
-};
 
 // {x, y, ca, cb} and {cc, op, ext(half2 hx,hy), id} views of a record
 __device__ __forceinline__ float2 rec_extent(const float4& r1)
@@ -62,5 +29,47 @@ __device__ __forceinline__ bool rec_hits_block(const float4& r0, const float4& r
 	const float2 e = rec_extent(r1);
 	return (e.x >= 0.f) && (r0.x + e.x >= x0) && (r0.x - e.x <= x1) && (r0.y + e.y >= y0) && (r0.y - e.y <= y1);
 }
+
+// Per-warp record ring.  All methods are called by the whole (converged) warp.
+struct WarpRecRing {
+	InstRec* buf;        // RING * REC_BATCH records
+	uint64_t* bar;       // RING mbarriers (count 1)
+	const InstRec* src;  // first record of the (sub)list this warp walks
+	int total;           // number of records to walk
+	bool reverse;        // walk from the back (backward pass): batch 0 is the LAST REC_BATCH-aligned block
+
+	__device__ __forceinline__ int num_batches() const { return (total + REC_BATCH - 1) / REC_BATCH; }
+	__device__ __forceinline__ int batch_lo(int k) const { return reverse ? REC_BATCH * (num_batches() - 1 - k) : REC_BATCH * k; }
+	__device__ __forceinline__ int batch_n(int k) const { return min(REC_BATCH, total - batch_lo(k)); }
+
+	__device__ __forceinline__ void init(InstRec* b, uint64_t* bars, const InstRec* s, int n, bool rev)
+	{
+		buf = b; bar = bars; src = s; total = n; reverse = rev;
+		if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+			for (int i = 0; i < RING; i++) mbar_init(&bar[i], 1);
+			mbar_fence_init();
+		}
+		__syncwarp();
+	}
+	// start the copy of batch k into buffer k % RING (the buffer's previous contents must be dead)
+	__device__ __forceinline__ void issue(int k)
+	{
+		__syncwarp();
+		if ((threadIdx.x & 31) == 0) {
+			const int b = k % RING, n = batch_n(k);
+			fence_proxy_async();
+			mbar_arrive_expect_tx(&bar[b], (uint32_t)n * (uint32_t)sizeof(InstRec));
+			bulk_g2s(buf + b * REC_BATCH, src + batch_lo(k), (uint32_t)n * (uint32_t)sizeof(InstRec), &bar[b]);
+		}
+	}
+	__device__ __forceinline__ const float4* wait(int k)
+	{
+		const int b = k % RING;
+		mbar_wait(&bar[b], (uint32_t)((k / RING) & 1));
+		return reinterpret_cast<const float4*>(buf + b * REC_BATCH);
+	}
+	__device__ __forceinline__ const float4* buffer(int k) const { return reinterpret_cast<const float4*>(buf + (k % RING) * REC_BATCH); }
+};
 
 }  // namespace mgs

@@ -34,6 +34,7 @@ struct ProjectFwdArgs {
 	float2* extent;
 	uint8_t* clamped;  // 3 bits per Gaussian
 	uint32_t* tiles_touched;
+	uint32_t* iota;    // identity permutation (values of the depth sort)
 };
 
 struct ProjectBwdArgs {
@@ -97,13 +98,17 @@ void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, u
 
 // binning.cu
 size_t scan_temp_bytes(int P);
-size_t sort_temp_bytes(int R);
-void launch_scan(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int P, cudaStream_t s);
-void launch_emit_keys(int P, const float2* means2D, const float* depths, const uint32_t* offsets, const int* radii,
-	uint32_t grid_x, uint32_t grid_y, uint64_t* keys, uint32_t* values, cudaStream_t s);
-void launch_sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
+size_t depth_sort_temp_bytes(int P);
+size_t tile_sort_temp_bytes(int R);
+void launch_depth_sort(void* temp, size_t temp_bytes, const uint32_t* depth_bits, uint32_t* depth_bits_sorted,
+	const uint32_t* iota, uint32_t* order, int P, cudaStream_t s);
+void launch_scan_sorted(void* temp, size_t temp_bytes, const uint32_t* order, const uint32_t* tiles_touched, uint32_t* offsets,
+	int P, cudaStream_t s);
+void launch_emit_tiles(int P, const uint32_t* order, const float2* means2D, const uint32_t* offsets, const int* radii,
+	uint32_t grid_x, uint32_t grid_y, uint32_t* tile_keys, uint32_t* values, cudaStream_t s);
+void launch_tile_sort(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
 	const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit, cudaStream_t s);
-void launch_ranges_and_pack(int R, int num_tiles, const uint64_t* keys, const uint32_t* point_list,
+void launch_ranges_and_pack(int R, int num_tiles, const uint32_t* tile_keys, const uint32_t* point_list,
 	const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs, cudaStream_t s);
 
 // blend_fwd.cu / blend_bwd.cu

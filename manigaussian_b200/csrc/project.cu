@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(256) project_fwd_kernel(ProjectFwdArgs a)
 	uint32_t out_tiles = 0;
 	a.radii[idx] = 0;
 	a.tiles_touched[idx] = 0;
+	a.iota[idx] = (uint32_t)idx;
+	a.depths[idx] = __uint_as_float(0x7f800000u);  // +inf: culled Gaussians sort behind every visible one
 
 	V3 p_orig = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
 	float4 p_hom = xform4x4(p_orig, a.projmatrix);

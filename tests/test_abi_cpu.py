@@ -31,7 +31,7 @@ def test_state_size_queries_are_monotone_and_aligned():
         assert b >= prev and b >= 79 * P
         prev = b
     assert L.mgs_image_state_bytes(256, 256) >= 256 * 256 * 8 + 256 * 8
-    assert L.mgs_binning_state_bytes(1000) >= 1000 * (4 + 4 + 8 + 8 + 32)
+    assert L.mgs_binning_state_bytes(1000) >= 1000 * (4 + 4 + 4 + 4 + 32)
     assert L.mgs_backward_scratch_bytes(10) >= 10 * 48
 
 

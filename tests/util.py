@@ -166,9 +166,13 @@ def run_ours(inp, backward=True, debug=False):
     fw["tiles_touched"] = fw["tiles_touched"].astype(np.uint32)
     Rn = num_rendered
     fw["point_list"] = arr("binning", "point_list", binB, Rn, 0, torch.int32, Rn).astype(np.uint32)
-    fw["point_list_keys"] = arr("binning", "point_list_keys", binB, Rn, 0, torch.int64, Rn).astype(np.uint64)
+    fw["tile_ids"] = arr("binning", "tile_ids", binB, Rn, 0, torch.int32, Rn).astype(np.uint32)
     fw["point_list_unsorted"] = arr("binning", "point_list_unsorted", binB, Rn, 0, torch.int32, Rn).astype(np.uint32)
-    fw["point_list_keys_unsorted"] = arr("binning", "point_list_keys_unsorted", binB, Rn, 0, torch.int64, Rn).astype(np.uint64)
+    fw["depth_order"] = arr("geometry", "depth_order", geomB, P, 0, torch.int32, P).astype(np.uint32)
+    # The library sorts (depth, id) then (tile) instead of one 64-bit key; the reference's key array is, by definition
+    # (rasterizer_impl.cu:100-104), tile << 32 | depth bits of the instance's Gaussian -- rebuilt here for comparison.
+    fw["point_list_keys"] = (fw["tile_ids"].astype(np.uint64) << np.uint64(32)) | \
+        fw["depths"].view(np.uint32)[fw["point_list"]].astype(np.uint64)
     fw["final_T"] = arr("image", "final_T", imgB, W, H, torch.float32, N)
     fw["n_contrib"] = arr("image", "n_contrib", imgB, W, H, torch.int32, N).astype(np.uint32)
     fw["ranges"] = arr("image", "ranges", imgB, W, H, torch.int32, 2 * T).astype(np.uint32).reshape(T, 2)
