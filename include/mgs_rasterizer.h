@@ -92,6 +92,51 @@ int mgs_forward(
 	void* stream);
 
 /*
+ * Split forward for multi-view batches (no reference counterpart: the reference renders one view per call and blocks
+ * the host on its instance count, rasterizer_impl.cu:284).  mgs_forward_begin enqueues the per-Gaussian projection,
+ * depth ordering and instance-offset scan of one view on `stream` and copies the instance count to
+ * *host_num_rendered (pinned host memory recommended) asynchronously; the caller may begin further views on other
+ * streams, then synchronises each stream and calls mgs_forward_finish with the count to enqueue binning and the
+ * blend.  mgs_forward == begin + stream sync + finish.  The geometry/image state of begin is passed back to finish.
+ */
+int mgs_forward_begin(
+	mgs_alloc_fn geometry_alloc, void* geometry_user,
+	mgs_alloc_fn image_alloc, void* image_user,
+	int P, int D, int M,
+	int width, int height,
+	const float* means3D,
+	const float* shs,
+	const float* colors_precomp,
+	const float* opacities,
+	const float* scales,
+	float scale_modifier,
+	const float* rotations,
+	const float* cov3D_precomp,
+	const float* viewmatrix,
+	const float* projmatrix,
+	const float* cam_pos,
+	float tan_fovx, float tan_fovy,
+	int* radii,
+	int* host_num_rendered,
+	int debug,
+	void* stream);
+int mgs_forward_finish(
+	mgs_alloc_fn binning_alloc, void* binning_user,
+	char* geometry_state,
+	char* image_state,
+	int P, int F,
+	int width, int height,
+	const float* background,
+	const float* feature_precomp,
+	const int* radii,
+	int num_rendered,
+	float* out_color,
+	float* out_feature,
+	float* out_depth,
+	int debug,
+	void* stream);
+
+/*
  * Backward.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:62-91, rasterizer_impl.cu:359-463).
  *   dL_dpix [3,H,W], dL_dpix_F [F,H,W] or NULL, dL_dpix_depth [H,W] or NULL.
  *   Outputs (each fully written; NULL allowed for dL_dconic, dL_dcolor, dL_dcov3D, dL_dsh, dL_dscale, dL_drot):

@@ -40,6 +40,11 @@ def lib():
                               f, f, i,               # tan_fovx tan_fovy prefiltered
                               vp, vp, vp, vp,        # out_color out_feature out_depth radii
                               i, vp]                 # debug stream
+    L.mgs_forward_begin.restype = C.c_int
+    L.mgs_forward_begin.argtypes = [ALLOC_FN, vp, ALLOC_FN, vp, i, i, i, i, i,
+                                    vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, f, f, vp, vp, i, vp]
+    L.mgs_forward_finish.restype = C.c_int
+    L.mgs_forward_finish.argtypes = [ALLOC_FN, vp, vp, vp, i, i, i, i, vp, vp, vp, i, vp, vp, vp, i, vp]
     L.mgs_backward.restype = C.c_int
     L.mgs_backward.argtypes = [i, i, i, i, i,        # P D M F R
                                vp, i, i,             # background width height
@@ -68,7 +73,8 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "mgs_abi_version", "mgs_last_error", "mgs_geometry_state_bytes", "mgs_image_state_bytes",
-    "mgs_binning_state_bytes", "mgs_backward_scratch_bytes", "mgs_forward", "mgs_backward",
+    "mgs_binning_state_bytes", "mgs_backward_scratch_bytes", "mgs_forward", "mgs_forward_begin", "mgs_forward_finish",
+    "mgs_backward",
     "mgs_mark_visible", "mgs_state_array", "mgs_profile_enable", "mgs_profile_num_stages",
     "mgs_profile_stage_name", "mgs_profile_read",
 )

@@ -177,50 +177,31 @@ size_t mgs_image_state_bytes(int width, int height)
 size_t mgs_binning_state_bytes(int R) { return required([&](char*& p) { BinState::carve(p, (size_t)R); }); }
 size_t mgs_backward_scratch_bytes(int P) { return (size_t)P * GB_STRIDE * sizeof(float) + 128; }
 
-int mgs_forward(
-	mgs_alloc_fn geometry_alloc, void* geometry_user,
-	mgs_alloc_fn binning_alloc, void* binning_user,
-	mgs_alloc_fn image_alloc, void* image_user,
-	int P, int D, int M, int F,
-	const float* background, int width, int height,
-	const float* means3D, const float* shs, const float* colors_precomp, const float* feature_precomp,
-	const float* opacities, const float* scales, float scale_modifier, const float* rotations,
-	const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
-	float tan_fovx, float tan_fovy, int prefiltered,
-	float* out_color, float* out_feature, float* out_depth, int* radii, int debug, void* stream)
+// ---- forward, phase 1: per-Gaussian projection, depth order, instance offsets; the instance count R is copied to
+// *host_num_rendered asynchronously on `st` (the caller synchronises before reading it) ----
+static int forward_phase1(
+	mgs_alloc_fn geometry_alloc, void* geometry_user, mgs_alloc_fn image_alloc, void* image_user,
+	int P, int D, int M, int width, int height,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+	float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+	const float* cam_pos, float tan_fovx, float tan_fovy, int* radii, int* host_num_rendered, int debug, cudaStream_t st,
+	char** geometry_state, char** image_state)
 {
-	(void)prefiltered;  // the reference only uses it to trap on inconsistent input (auxiliary.h:156-160)
-	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-	if (P < 0 || width <= 0 || height <= 0) return fail(MGS_ERR_INVALID_ARG, "bad P/width/height");
-	if (!geometry_alloc || !binning_alloc || !image_alloc) return fail(MGS_ERR_INVALID_ARG, "allocator callbacks are required");
-	if (!out_color || !background) return fail(MGS_ERR_INVALID_ARG, "out_color/background are required");
-	if (F < 0 || F > MGS_MAX_FEATURE_CHANNELS || !blend_supported(F))
-		return fail(MGS_ERR_UNSUPPORTED, "feature channel count must be in [0, 32]");
-	if (F > 0 && (!feature_precomp || !out_feature)) F = 0;  // include_feature == false
-	const size_t N = (size_t)width * height;
-	if (P == 0) {
-		// reference: outputs keep their zero fill when there are no Gaussians (rasterize_points.cu:70-92)
-		MGS_CUDA(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), st));
-		if (F > 0) MGS_CUDA(cudaMemsetAsync(out_feature, 0, (size_t)F * N * sizeof(float), st));
-		if (out_depth) MGS_CUDA(cudaMemsetAsync(out_depth, 0, N * sizeof(float), st));
-		return 0;
-	}
 	if (!means3D || !opacities || !viewmatrix || !projmatrix || !radii)
 		return fail(MGS_ERR_INVALID_ARG, "means3D/opacities/viewmatrix/projmatrix/radii are required");
 	if (!colors_precomp && !shs) return fail(MGS_ERR_INVALID_ARG, "provide SHs or precomputed colours");
 	if (!colors_precomp && !cam_pos) return fail(MGS_ERR_INVALID_ARG, "cam_pos is required with SHs");
 	if (!cov3D_precomp && (!scales || !rotations)) return fail(MGS_ERR_INVALID_ARG, "provide scales+rotations or a precomputed 3D covariance");
-
 	const float focal_y = height / (2.0f * tan_fovy);  // rasterizer_impl.cu:225-226
 	const float focal_x = width / (2.0f * tan_fovx);
 	const int gx = ceil_div(width, TILE_X), gy = ceil_div(height, TILE_Y);
-	const size_t T = (size_t)gx * gy;
 
 	char* gchunk = geometry_alloc(geometry_user, mgs_geometry_state_bytes(P));
 	char* ichunk = image_alloc(image_user, mgs_image_state_bytes(width, height));
 	if (!gchunk || !ichunk) return fail(MGS_ERR_ALLOC, "state allocation failed");
+	*geometry_state = gchunk;
+	*image_state = ichunk;
 	GeomState geom = GeomState::carve(gchunk, (size_t)P);
-	ImageState img = ImageState::carve(ichunk, N, T);
 
 	ProjectFwdArgs pa{};
 	pa.P = P; pa.D = D; pa.M = M;
@@ -244,11 +225,21 @@ int mgs_forward(
 	MGS_STAGE("depth_sort");
 	{ StageTimer t_(ST_SCAN, st); launch_scan_sorted(geom.temp, geom.temp_bytes, geom.order, geom.tiles_touched, geom.point_offsets, P, st); }
 	MGS_STAGE("scan");
+	MGS_CUDA(cudaMemcpyAsync(host_num_rendered, geom.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+	return 0;
+}
 
-	int num_rendered = 0;
-	MGS_CUDA(cudaMemcpyAsync(&num_rendered, geom.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-	MGS_CUDA(cudaStreamSynchronize(st));
+// ---- forward, phase 2: instance emission, per-tile order, records, blend ----
+static int forward_phase2(
+	mgs_alloc_fn binning_alloc, void* binning_user, char* geometry_state, char* image_state,
+	int P, int F, int width, int height, const float* background, const float* feature_precomp, const int* radii,
+	int num_rendered, float* out_color, float* out_feature, float* out_depth, int debug, cudaStream_t st)
+{
 	if (num_rendered < 0) return fail(MGS_ERR_UNSUPPORTED, "more than 2^31-1 tile instances");
+	const int gx = ceil_div(width, TILE_X), gy = ceil_div(height, TILE_Y);
+	const size_t N = (size_t)width * height, T = (size_t)gx * gy;
+	GeomState geom = GeomState::carve(geometry_state, (size_t)P);
+	ImageState img = ImageState::carve(image_state, N, T);
 
 	char* bchunk = binning_alloc(binning_user, mgs_binning_state_bytes(num_rendered));
 	if (!bchunk) return fail(MGS_ERR_ALLOC, "binning state allocation failed");
@@ -284,6 +275,83 @@ int mgs_forward(
 	{ StageTimer t_(ST_BLEND_FWD, st); launch_blend_fwd(ba, st); }
 	MGS_STAGE("blend_fwd");
 	return num_rendered;
+}
+
+static int forward_check(int P, int width, int height, int& F, const float* background, const float* feature_precomp,
+	float* out_color, float* out_feature)
+{
+	if (P < 0 || width <= 0 || height <= 0) return fail(MGS_ERR_INVALID_ARG, "bad P/width/height");
+	if (!out_color || !background) return fail(MGS_ERR_INVALID_ARG, "out_color/background are required");
+	if (F < 0 || F > MGS_MAX_FEATURE_CHANNELS || !blend_supported(F))
+		return fail(MGS_ERR_UNSUPPORTED, "feature channel count must be in [0, 32]");
+	if (F > 0 && (!feature_precomp || !out_feature)) F = 0;  // include_feature == false
+	return 0;
+}
+
+int mgs_forward(
+	mgs_alloc_fn geometry_alloc, void* geometry_user,
+	mgs_alloc_fn binning_alloc, void* binning_user,
+	mgs_alloc_fn image_alloc, void* image_user,
+	int P, int D, int M, int F,
+	const float* background, int width, int height,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* feature_precomp,
+	const float* opacities, const float* scales, float scale_modifier, const float* rotations,
+	const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+	float tan_fovx, float tan_fovy, int prefiltered,
+	float* out_color, float* out_feature, float* out_depth, int* radii, int debug, void* stream)
+{
+	(void)prefiltered;  // the reference only uses it to trap on inconsistent input (auxiliary.h:156-160)
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	if (!geometry_alloc || !binning_alloc || !image_alloc) return fail(MGS_ERR_INVALID_ARG, "allocator callbacks are required");
+	int rc = forward_check(P, width, height, F, background, feature_precomp, out_color, out_feature);
+	if (rc < 0) return rc;
+	const size_t N = (size_t)width * height;
+	if (P == 0) {
+		// reference: outputs keep their zero fill when there are no Gaussians (rasterize_points.cu:70-92)
+		MGS_CUDA(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), st));
+		if (F > 0) MGS_CUDA(cudaMemsetAsync(out_feature, 0, (size_t)F * N * sizeof(float), st));
+		if (out_depth) MGS_CUDA(cudaMemsetAsync(out_depth, 0, N * sizeof(float), st));
+		return 0;
+	}
+	char *gstate = nullptr, *istate = nullptr;
+	int num_rendered = 0;
+	rc = forward_phase1(geometry_alloc, geometry_user, image_alloc, image_user, P, D, M, width, height, means3D, shs, colors_precomp,
+		opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, radii,
+		&num_rendered, debug, st, &gstate, &istate);
+	if (rc < 0) return rc;
+	MGS_CUDA(cudaStreamSynchronize(st));  // the one host sync of the forward, as in the reference (rasterizer_impl.cu:284)
+	return forward_phase2(binning_alloc, binning_user, gstate, istate, P, F, width, height, background, feature_precomp, radii,
+		num_rendered, out_color, out_feature, out_depth, debug, st);
+}
+
+int mgs_forward_begin(
+	mgs_alloc_fn geometry_alloc, void* geometry_user, mgs_alloc_fn image_alloc, void* image_user,
+	int P, int D, int M, int width, int height,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+	float scale_modifier, const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+	const float* cam_pos, float tan_fovx, float tan_fovy, int* radii, int* host_num_rendered, int debug, void* stream)
+{
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	if (P <= 0 || width <= 0 || height <= 0) return fail(MGS_ERR_INVALID_ARG, "bad P/width/height (P must be > 0)");
+	if (!geometry_alloc || !image_alloc || !host_num_rendered) return fail(MGS_ERR_INVALID_ARG, "allocators and host_num_rendered are required");
+	char *gstate = nullptr, *istate = nullptr;
+	return forward_phase1(geometry_alloc, geometry_user, image_alloc, image_user, P, D, M, width, height, means3D, shs, colors_precomp,
+		opacities, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, radii,
+		host_num_rendered, debug, st, &gstate, &istate);
+}
+
+int mgs_forward_finish(
+	mgs_alloc_fn binning_alloc, void* binning_user, char* geometry_state, char* image_state,
+	int P, int F, int width, int height, const float* background, const float* feature_precomp, const int* radii,
+	int num_rendered, float* out_color, float* out_feature, float* out_depth, int debug, void* stream)
+{
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	if (!binning_alloc || !geometry_state || !image_state || !radii) return fail(MGS_ERR_INVALID_ARG, "required pointer is NULL");
+	int rc = forward_check(P, width, height, F, background, feature_precomp, out_color, out_feature);
+	if (rc < 0) return rc;
+	if (P == 0) return fail(MGS_ERR_INVALID_ARG, "P must be > 0");
+	return forward_phase2(binning_alloc, binning_user, geometry_state, image_state, P, F, width, height, background, feature_precomp,
+		radii, num_rendered, out_color, out_feature, out_depth, debug, st);
 }
 
 int mgs_backward(

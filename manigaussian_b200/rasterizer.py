@@ -328,3 +328,106 @@ class GaussianRasterizer(nn.Module):
         cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, language_feature_precomp, opacities, scales,
                                    rotations, cov3D_precomp, self.raster_settings, self.return_depth)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Multi-view batches (no counterpart in the reference, which renders one view per call and
+# blocks the host on every view's instance count).  All views share one Gaussian cloud; each view is enqueued on its own
+# CUDA stream through the split forward of the C ABI (mgs_forward_begin / mgs_forward_finish), so the projection and
+# binning chains of all views are in flight before the host waits for the first instance count, and the blend kernels
+# of different views overlap on the GPU.
+_VIEW_STREAMS = {}
+_PINNED_COUNTS = {}
+
+
+def _view_streams(device, n):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    pool = _VIEW_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        sh, degree, include_feature, return_depth=False, debug=False, after_view=None):
+    """Forward of V views of one Gaussian cloud.  `views` is a sequence of GaussianRasterizationSettings (bg, viewmatrix,
+    projmatrix, tanfov*, image size, campos are read per view).  Returns (outs, streams): outs[v] has the layout of
+    rasterize_gaussians_raw's result; work of view v is enqueued on streams[v] (callers that consume the outputs on
+    another stream must wait on it; rasterize_views_backward_raw does).  `after_view(v, out)` is called inside view v's
+    stream context as soon as its forward is enqueued (e.g. to enqueue that view's backward before finishing the next view)."""
+    L = _b.lib()
+    dev = means3D.device
+    if not means3D.is_cuda:
+        raise RuntimeError("manigaussian_b200 runs on CUDA tensors only (there is no CPU path)")
+    P = means3D.size(0)
+    if P == 0:
+        raise RuntimeError("rasterize_views_raw needs at least one Gaussian")
+    means3D, colors, language_feature, opacity = (_prep(x, dev) for x in (means3D, colors, language_feature, opacity))
+    scales, rotations, cov3D_precomp, sh = (_prep(x, dev) for x in (scales, rotations, cov3D_precomp, sh))
+    F = language_feature.size(1) if (include_feature and language_feature is not None and language_feature.numel() > 0) else 0
+    M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
+    V = len(views)
+    streams = _view_streams(dev, V)
+    main = torch.cuda.current_stream(dev)
+    counts = _PINNED_COUNTS.get(V)
+    if counts is None or counts.numel() < V:
+        counts = torch.zeros(max(V, 8), dtype=torch.int32).pin_memory()
+        _PINNED_COUNTS[V] = counts
+    pend = []
+    with torch.cuda.device(dev):
+        for v, s in enumerate(views):
+            st = streams[v]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                H, W = int(s.image_height), int(s.image_width)
+                bg, vm, pm, cp = (_prep(x, dev) for x in (s.bg, s.viewmatrix, s.projmatrix, s.campos))
+                radii = torch.empty((P,), dtype=torch.int32, device=dev)
+                ga, ia, ba = _Alloc(dev), _Alloc(dev), _Alloc(dev)
+                _b.check(L.mgs_forward_begin(
+                    _ALLOC_CB, ga.key, _ALLOC_CB, ia.key, P, int(degree), M, W, H,
+                    _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                    _ptr(cov3D_precomp), _ptr(vm), _ptr(pm), _ptr(cp), float(s.tanfovx), float(s.tanfovy), _ptr(radii),
+                    counts.data_ptr() + 4 * v, int(bool(debug)), st.cuda_stream), "mgs_forward_begin")
+                pend.append((st, H, W, bg, vm, pm, cp, radii, ga, ia, ba))
+        outs = []
+        for v, (st, H, W, bg, vm, pm, cp, radii, ga, ia, ba) in enumerate(pend):
+            st.synchronize()
+            R = int(counts[v])
+            with torch.cuda.stream(st):
+                out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+                out_feature = torch.empty((F, H, W), dtype=torch.float32, device=dev) if include_feature else \
+                    torch.zeros((1,), dtype=torch.float32, device=dev)
+                out_depth = torch.empty((H, W), dtype=torch.float32, device=dev) if return_depth else None
+                geom, img = ga.release(), ia.release()
+                _b.check(L.mgs_forward_finish(
+                    _ALLOC_CB, ba.key, _ptr(geom), _ptr(img), P, F, W, H, _ptr(bg), _ptr(language_feature) if F else None,
+                    _ptr(radii), R, _ptr(out_color), _ptr(out_feature) if F else None, _ptr(out_depth), int(bool(debug)),
+                    st.cuda_stream), "mgs_forward_finish")
+                ret = (R, out_color, out_feature, radii, geom, ba.release(), img)
+                outs.append(ret + (out_depth,) if return_depth else ret)
+                if after_view is not None:
+                    after_view(v, outs[-1])  # still inside view v's stream context: e.g. enqueue its backward right away
+    return outs, streams
+
+
+def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_feature, means3D, colors, language_feature, scales,
+                                 rotations, scale_modifier, cov3D_precomp, sh, degree, include_feature, grads_depth=None,
+                                 debug=False):
+    """Backward of the V views rendered by rasterize_views_raw, each on its view's stream.  Returns a list of the
+    9-tuples of rasterize_gaussians_backward_raw.  The caller's current stream waits for all of them on return."""
+    dev = means3D.device
+    main = torch.cuda.current_stream(dev)
+    res = []
+    for v, s in enumerate(views):
+        st = streams[v]
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            o = outs[v]
+            res.append(rasterize_gaussians_backward_raw(
+                s.bg, means3D, o[3], colors, language_feature, scales, rotations, scale_modifier, cov3D_precomp, s.viewmatrix,
+                s.projmatrix, s.tanfovx, s.tanfovy, grads_color[v], grads_feature[v] if grads_feature is not None else None, sh,
+                degree, s.campos, o[4], o[0], o[5], o[6], debug, include_feature,
+                dL_dout_depth=grads_depth[v] if grads_depth is not None else None))
+    for st in streams[:len(views)]:
+        main.wait_stream(st)
+    return res
