@@ -213,11 +213,46 @@ def make_packed(P, F, M, torch):
     return pk.flat, pk.views
 
 
+def run_step_views(G, C, T, flat, acc, dist, F, depth):
+    """ours, multi-view entry points: all views' projection/binning chains are in flight before the host waits for the first
+    instance count; blends of different views overlap (manigaussian_b200.rasterizer.rasterize_views_raw)."""
+    import torch
+    from manigaussian_b200 import rasterizer as R
+    from manigaussian_b200 import GaussianRasterizationSettings as S
+    if "settings" not in G:
+        G["settings"] = [S(c["H"], c["W"], c["tanfovx"], c["tanfovy"], c["bg"], 1.0, c["viewmatrix"], c["projmatrix"], SH_DEGREE,
+                           c["campos"], False, False, F > 0) for c in C]
+    views = G["settings"]
+    flat.zero_()
+    outs, sts = R.rasterize_views_raw(views, G["means3D"], G["empty"], G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0,
+                                      G["empty"], G["shs"], SH_DEGREE, F > 0, return_depth=depth)
+    grads = R.rasterize_views_backward_raw(views, outs, sts, [t["dL_dcolor"] for t in T],
+                                           [t["dL_dfeature"] for t in T] if F else None, G["means3D"], G["empty"], G["feature"],
+                                           G["scales"], G["rotations"], 1.0, G["empty"], G["shs"], SH_DEGREE, F > 0,
+                                           grads_depth=[t["dL_ddepth"] for t in T] if depth else None)
+    main = torch.cuda.current_stream()
+    Rs = 0
+    for o, g9 in zip(outs, grads):
+        Rs += int(o[0])
+        gd = dict(zip(GRAD_ORDER, g9))
+        for k, v in acc.items():
+            gd[k].record_stream(main)
+            v.add_(gd[k].reshape(v.shape))
+        for t in o:
+            if hasattr(t, "record_stream"):
+                t.record_stream(main)
+    if dist is not None:
+        dist.all_reduce(flat)
+    return Rs
+
+
 def run_step(impl, G, C, T, flat, acc, dist=None, streams=None):
     """One step: fwd+bwd of every local view, gradients summed into the packed buffer, one all-reduce.
     With `streams` (ours only: the C ABI takes the caller's stream) independent views are enqueued on different CUDA
     streams so their kernels overlap; the reference launches on the legacy default stream and cannot."""
     import torch
+    if streams and impl.name == "ours":
+        return run_step_views(G, C, T, flat, acc, dist, impl.F, impl.depth)
     flat.zero_()
     Rs = 0
     if not streams:
