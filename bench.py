@@ -226,18 +226,16 @@ def run_step_views(G, C, T, flat, acc, dist, F, depth):
     flat.zero_()
     outs, sts = R.rasterize_views_raw(views, G["means3D"], G["empty"], G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0,
                                       G["empty"], G["shs"], SH_DEGREE, F > 0, return_depth=depth)
-    grads = R.rasterize_views_backward_raw(views, outs, sts, [t["dL_dcolor"] for t in T],
-                                           [t["dL_dfeature"] for t in T] if F else None, G["means3D"], G["empty"], G["feature"],
-                                           G["scales"], G["rotations"], 1.0, G["empty"], G["shs"], SH_DEGREE, F > 0,
-                                           grads_depth=[t["dL_ddepth"] for t in T] if depth else None)
+    # every view's backward ADDS its gradients straight into the packed buffer (the all-reduce message): no per-view
+    # gradient tensors, no elementwise accumulation kernels
+    R.rasterize_views_backward_raw(views, outs, sts, [t["dL_dcolor"] for t in T],
+                                   [t["dL_dfeature"] for t in T] if F else None, G["means3D"], G["empty"], G["feature"],
+                                   G["scales"], G["rotations"], 1.0, G["empty"], G["shs"], SH_DEGREE, F > 0,
+                                   grads_depth=[t["dL_ddepth"] for t in T] if depth else None, accumulate_into=acc)
     main = torch.cuda.current_stream()
     Rs = 0
-    for o, g9 in zip(outs, grads):
+    for o in outs:
         Rs += int(o[0])
-        gd = dict(zip(GRAD_ORDER, g9))
-        for k, v in acc.items():
-            gd[k].record_stream(main)
-            v.add_(gd[k].reshape(v.shape))
         for t in o:
             if hasattr(t, "record_stream"):
                 t.record_stream(main)

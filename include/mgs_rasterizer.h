@@ -144,6 +144,10 @@ int mgs_forward_finish(
  *     dL_dcolor [P,3], dL_dfeature [P,F], dL_dmean3D [P,3], dL_dcov3D [P,6], dL_dsh [P,M,3],
  *     dL_dscale [P,3], dL_drot [P,4].
  *   blend_scratch: device scratch of mgs_backward_scratch_bytes(P) bytes (contents irrelevant on entry).
+ *   accumulate: 0 = every output row is written exactly once (the reference's semantics after its zero-fill);
+ *               1 = every output is ADDED into the caller's buffer with L2 reductions (red.global.add), so several
+ *                   views, possibly on different streams, can sum straight into one packed gradient buffer -- the
+ *                   message of the multi-GPU all-reduce -- without intermediate tensors (no reference counterpart).
  */
 size_t mgs_backward_scratch_bytes(int P);
 int mgs_backward(
@@ -180,6 +184,7 @@ int mgs_backward(
 	float* dL_dscale,
 	float* dL_drot,
 	char* blend_scratch,
+	int accumulate,
 	int debug,
 	void* stream);
 

@@ -55,7 +55,7 @@ def lib():
                                vp, vp, vp,           # dL_dpix dL_dpix_F dL_dpix_depth
                                vp, vp, vp, vp, vp,   # dL_dmean2D dL_dconic dL_dopacity dL_dcolor dL_dfeature
                                vp, vp, vp, vp, vp,   # dL_dmean3D dL_dcov3D dL_dsh dL_dscale dL_drot
-                               vp, i, vp]            # scratch debug stream
+                               vp, i, i, vp]         # scratch accumulate debug stream
     L.mgs_mark_visible.restype = C.c_int
     L.mgs_mark_visible.argtypes = [i, vp, vp, vp, vp, vp]
     L.mgs_state_array.restype = C.c_int
@@ -65,7 +65,7 @@ def lib():
     L.mgs_profile_stage_name.restype = C.c_char_p
     L.mgs_profile_stage_name.argtypes = [i]
     L.mgs_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
-    if L.mgs_abi_version() != 100:
+    if L.mgs_abi_version() != 101:
         raise ImportError("manigaussian_b200: ABI version mismatch")
     _lib = L
     return L

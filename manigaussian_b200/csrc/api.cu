@@ -166,7 +166,7 @@ using namespace mgs;
 
 extern "C" {
 
-int mgs_abi_version(void) { return 100; }
+int mgs_abi_version(void) { return 101; }
 const char* mgs_last_error(void) { return g_err.c_str(); }
 
 size_t mgs_geometry_state_bytes(int P) { return required([&](char*& p) { GeomState::carve(p, (size_t)P); }); }
@@ -364,7 +364,7 @@ int mgs_backward(
 	const float* dL_dpix, const float* dL_dpix_F, const float* dL_dpix_depth,
 	float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dfeature,
 	float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
-	char* blend_scratch, int debug, void* stream)
+	char* blend_scratch, int accumulate, int debug, void* stream)
 {
 	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 	if (P < 0 || width <= 0 || height <= 0 || R < 0) return fail(MGS_ERR_INVALID_ARG, "bad P/R/width/height");
@@ -387,7 +387,7 @@ int mgs_backward(
 	float* gb = nullptr;
 	obtain(blend_scratch, gb, (size_t)P * GB_STRIDE);
 	MGS_CUDA(cudaMemsetAsync(gb, 0, (size_t)P * GB_STRIDE * sizeof(float), st));
-	if (F > 0) MGS_CUDA(cudaMemsetAsync(dL_dfeature, 0, (size_t)P * F * sizeof(float), st));
+	if (F > 0 && !accumulate) MGS_CUDA(cudaMemsetAsync(dL_dfeature, 0, (size_t)P * F * sizeof(float), st));
 
 	BlendArgs ba{};
 	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F; ba.nq = nq_for(F);
@@ -409,7 +409,7 @@ int mgs_backward(
 	pb.cov3D = geom.cov3D; pb.cov3D_precomp = cov3D_precomp;
 	pb.viewmatrix = viewmatrix; pb.projmatrix = projmatrix; pb.cam_pos = campos;
 	pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy; pb.focal_x = focal_x; pb.focal_y = focal_y;
-	pb.gb = gb;
+	pb.gb = gb; pb.accumulate = accumulate;
 	pb.dL_dmean2D = dL_dmean2D; pb.dL_dconic = dL_dconic; pb.dL_dopacity = dL_dopacity; pb.dL_dcolor = dL_dcolor;
 	pb.dL_dmean3D = dL_dmean3D; pb.dL_dcov3D = dL_dcov3D; pb.dL_dsh = shs ? dL_dsh : nullptr;
 	pb.dL_dscale = dL_dscale; pb.dL_drot = dL_drot; pb.dL_ddepth = nullptr;

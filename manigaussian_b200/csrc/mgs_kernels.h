@@ -53,6 +53,7 @@ struct ProjectBwdArgs {
 	const float* cam_pos;
 	float tan_fovx, tan_fovy, focal_x, focal_y;
 	const float* gb;  // [P, GB_STRIDE] blend-stage gradients
+	int accumulate;   // 0: every output row is written once; 1: outputs are summed into with L2 reductions
 	// outputs (each row written exactly once; nullable where noted)
 	float* dL_dmean2D;  // [P,3]
 	float* dL_dconic;   // [P,4] nullable

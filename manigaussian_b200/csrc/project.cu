@@ -228,10 +228,16 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(ProjectBwdArgs a)
 	const float ddepth = g2.y;
 
 	// plain copies of blend-stage gradients into the reference's output tensors
-	a.dL_dmean2D[3 * idx + 0] = dmx; a.dL_dmean2D[3 * idx + 1] = dmy; a.dL_dmean2D[3 * idx + 2] = 0.f;
-	if (a.dL_dconic) { float4 c4 = make_float4(dca, dcb, 0.f, dcc); reinterpret_cast<float4*>(a.dL_dconic)[idx] = c4; }
-	a.dL_dopacity[idx] = dop;
-	if (a.dL_dcolor) { a.dL_dcolor[3 * idx] = dcol[0]; a.dL_dcolor[3 * idx + 1] = dcol[1]; a.dL_dcolor[3 * idx + 2] = dcol[2]; }
+	// accumulate mode (multi-view batches): outputs are SUMMED into the caller's buffers with L2 reductions, so several
+	// views -- on different streams -- can write straight into one packed gradient buffer (the all-reduce message)
+	const bool acc = a.accumulate != 0;
+	if (acc && !live) return;
+	auto put = [acc](float* p, float v) { if (acc) red_add(p, v); else *p = v; };
+	put(a.dL_dmean2D + 3 * idx + 0, dmx); put(a.dL_dmean2D + 3 * idx + 1, dmy);
+	if (!acc) a.dL_dmean2D[3 * idx + 2] = 0.f;
+	if (a.dL_dconic) { put(a.dL_dconic + 4 * idx, dca); put(a.dL_dconic + 4 * idx + 1, dcb); if (!acc) a.dL_dconic[4 * idx + 2] = 0.f; put(a.dL_dconic + 4 * idx + 3, dcc); }
+	put(a.dL_dopacity + idx, dop);
+	if (a.dL_dcolor) { put(a.dL_dcolor + 3 * idx, dcol[0]); put(a.dL_dcolor + 3 * idx + 1, dcol[1]); put(a.dL_dcolor + 3 * idx + 2, dcol[2]); }
 
 	float dmean[3] = { 0.f, 0.f, 0.f };
 	float dcov[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(ProjectBwdArgs a)
 			for (int c = 0; c < 3; c++) dRGB[c] = dcol[c] * (((cl >> c) & 1) ? 0.f : 1.f);
 			float dRGBdx[3] = { 0, 0, 0 }, dRGBdy[3] = { 0, 0, 0 }, dRGBdz[3] = { 0, 0, 0 };
 #define SHK(k) sh[3 * (k) + c]
-#define DSH(k, v) { float v_ = (v); _Pragma("unroll") for (int c = 0; c < 3; c++) dsh[3 * (k) + c] = v_ * dRGB[c]; }
+#define DSH(k, v) { float v_ = (v); _Pragma("unroll") for (int c = 0; c < 3; c++) put(&dsh[3 * (k) + c], v_ * dRGB[c]); }
 			DSH(0, kSH_C0);
 			if (deg > 0) {
 				float dRGBdsh1 = -kSH_C1 * y;
@@ -384,7 +390,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(ProjectBwdArgs a)
 			// coefficients above the active degree receive no gradient (the reference leaves its zeros)
 			{
 				const int used = (deg + 1) * (deg + 1);
-				for (int k = used; k < M; k++) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+				if (!acc) for (int k = used; k < M; k++) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
 			}
 #undef SHK
 #undef DSH
@@ -429,13 +435,18 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(ProjectBwdArgs a)
 		}
 	}
 
-	a.dL_dmean3D[3 * idx] = dmean[0]; a.dL_dmean3D[3 * idx + 1] = dmean[1]; a.dL_dmean3D[3 * idx + 2] = dmean[2];
+	put(a.dL_dmean3D + 3 * idx, dmean[0]); put(a.dL_dmean3D + 3 * idx + 1, dmean[1]); put(a.dL_dmean3D + 3 * idx + 2, dmean[2]);
 	if (a.dL_dcov3D) {
 #pragma unroll
-		for (int i = 0; i < 6; i++) a.dL_dcov3D[6 * (size_t)idx + i] = dcov[i];
+		for (int i = 0; i < 6; i++) put(a.dL_dcov3D + 6 * (size_t)idx + i, dcov[i]);
 	}
-	if (a.dL_dscale) { a.dL_dscale[3 * idx] = dscale[0]; a.dL_dscale[3 * idx + 1] = dscale[1]; a.dL_dscale[3 * idx + 2] = dscale[2]; }
-	if (a.dL_drot) reinterpret_cast<float4*>(a.dL_drot)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+	if (a.dL_dscale) { put(a.dL_dscale + 3 * idx, dscale[0]); put(a.dL_dscale + 3 * idx + 1, dscale[1]); put(a.dL_dscale + 3 * idx + 2, dscale[2]); }
+	if (a.dL_drot) {
+		float* dr = a.dL_drot + 4 * (size_t)idx;
+		if ((reinterpret_cast<uintptr_t>(dr) & 15) != 0) { put(dr, drot[0]); put(dr + 1, drot[1]); put(dr + 2, drot[2]); put(dr + 3, drot[3]); }
+		else if (acc) red_add_v4(dr, drot[0], drot[1], drot[2], drot[3]);
+		else *reinterpret_cast<float4*>(dr) = make_float4(drot[0], drot[1], drot[2], drot[3]);
+	}
 	if (a.dL_ddepth) a.dL_ddepth[idx] = ddepth;
 }
 

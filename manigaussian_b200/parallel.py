@@ -21,13 +21,13 @@ class PackedGradients:
     def __init__(self, P, F, M, device):
         self.widths = dict(dL_dmeans3D=3, dL_dmeans2D=3, dL_dscales=3, dL_drotations=4, dL_dopacity=1, dL_dsh=3 * M, dL_dfeature=F)
         self.P = P
-        self.flat = torch.zeros(P * sum(self.widths.values()), dtype=torch.float32, device=device)
-        self.views, off = {}, 0
+        # every field starts on a 16-byte boundary so that 128-bit reductions can target it directly
+        offs, off = {}, 0
         for k in FIELDS:
-            n = P * self.widths[k]
-            if n:
-                self.views[k] = self.flat[off:off + n].view(P, self.widths[k])
-            off += n
+            offs[k] = off
+            off += (P * self.widths[k] + 3) // 4 * 4
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.views = {k: self.flat[offs[k]:offs[k] + P * self.widths[k]].view(P, self.widths[k]) for k in FIELDS if self.widths[k]}
 
     @property
     def bytes_per_gaussian(self):

@@ -134,10 +134,14 @@ def rasterize_gaussians_raw(bg, means3D, colors, language_feature, opacity, scal
 def rasterize_gaussians_backward_raw(bg, means3D, radii, colors, language_feature, scales, rotations, scale_modifier,
                                      cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color,
                                      dL_dout_language_feature, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                     imageBuffer, debug, include_feature, dL_dout_depth=None):
+                                     imageBuffer, debug, include_feature, dL_dout_depth=None, accumulate_into=None):
     """Same contract as the reference's `_C.rasterize_gaussians_backward` (DGR/rasterize_points.cu:131-225):
     returns (dL_dmeans2D, dL_dcolors, dL_dlanguage_feature, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh,
-    dL_dscales, dL_drotations)."""
+    dL_dscales, dL_drotations).
+
+    accumulate_into: optional dict of preallocated fp32 tensors keyed like manigaussian_b200.parallel.FIELDS
+    (dL_dmeans3D, dL_dmeans2D, dL_dscales, dL_drotations, dL_dopacity, dL_dsh, dL_dfeature); the gradients of this view
+    are then ADDED into them on the device (C ABI `accumulate=1`) and the same tensors are returned."""
     L = _b.lib()
     dev = means3D.device
     P = means3D.size(0)
@@ -153,15 +157,23 @@ def rasterize_gaussians_backward_raw(bg, means3D, radii, colors, language_featur
         dL_dout_language_feature = _prep(dL_dout_language_feature, dev)
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
     opts = dict(dtype=torch.float32, device=dev)
-    dL_dmeans3D = torch.empty((P, 3), **opts)
-    dL_dmeans2D = torch.empty((P, 3), **opts)
-    dL_dcolors = torch.empty((P, 3), **opts)
-    dL_dfeature = torch.empty((P, F), **opts) if F else torch.zeros((1,), **opts)
-    dL_dopacity = torch.empty((P, 1), **opts)
-    dL_dcov3D = torch.empty((P, 6), **opts)
-    dL_dsh = torch.empty((P, M, 3), **opts)
-    dL_dscales = torch.empty((P, 3), **opts)
-    dL_drotations = torch.empty((P, 4), **opts)
+    acc = accumulate_into
+    if acc is not None:
+        dL_dmeans3D, dL_dmeans2D, dL_dopacity = acc["dL_dmeans3D"], acc["dL_dmeans2D"], acc["dL_dopacity"]
+        dL_dscales, dL_drotations = acc.get("dL_dscales"), acc.get("dL_drotations")
+        dL_dsh = acc.get("dL_dsh") if M else torch.empty((P, 0, 3), **opts)
+        dL_dfeature = acc.get("dL_dfeature") if F else torch.zeros((1,), **opts)
+        dL_dcolors, dL_dcov3D = None, None
+    else:
+        dL_dmeans3D = torch.empty((P, 3), **opts)
+        dL_dmeans2D = torch.empty((P, 3), **opts)
+        dL_dcolors = torch.empty((P, 3), **opts)
+        dL_dfeature = torch.empty((P, F), **opts) if F else torch.zeros((1,), **opts)
+        dL_dopacity = torch.empty((P, 1), **opts)
+        dL_dcov3D = torch.empty((P, 6), **opts)
+        dL_dsh = torch.empty((P, M, 3), **opts)
+        dL_dscales = torch.empty((P, 3), **opts)
+        dL_drotations = torch.empty((P, 4), **opts)
     if P != 0:
         scratch = torch.empty((L.mgs_backward_scratch_bytes(P),), dtype=torch.uint8, device=dev)
         has_sr = scales is not None and scales.numel() != 0
@@ -177,8 +189,8 @@ def rasterize_gaussians_backward_raw(bg, means3D, radii, colors, language_featur
                 _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dfeature) if F else None,
                 _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh) if M else None,
                 _ptr(dL_dscales) if has_sr else None, _ptr(dL_drotations) if has_sr else None,
-                _ptr(scratch), int(bool(debug)), _stream(dev)), "mgs_backward")
-        if not has_sr:
+                _ptr(scratch), int(acc is not None), int(bool(debug)), _stream(dev)), "mgs_backward")
+        if not has_sr and acc is None:
             dL_dscales.zero_()
             dL_drotations.zero_()
     return (dL_dmeans2D, dL_dcolors, dL_dfeature, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
@@ -412,7 +424,7 @@ def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scale
 
 def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_feature, means3D, colors, language_feature, scales,
                                  rotations, scale_modifier, cov3D_precomp, sh, degree, include_feature, grads_depth=None,
-                                 debug=False):
+                                 debug=False, accumulate_into=None):
     """Backward of the V views rendered by rasterize_views_raw, each on its view's stream.  Returns a list of the
     9-tuples of rasterize_gaussians_backward_raw.  The caller's current stream waits for all of them on return."""
     dev = means3D.device
@@ -427,7 +439,7 @@ def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_featur
                 s.bg, means3D, o[3], colors, language_feature, scales, rotations, scale_modifier, cov3D_precomp, s.viewmatrix,
                 s.projmatrix, s.tanfovx, s.tanfovy, grads_color[v], grads_feature[v] if grads_feature is not None else None, sh,
                 degree, s.campos, o[4], o[0], o[5], o[6], debug, include_feature,
-                dL_dout_depth=grads_depth[v] if grads_depth is not None else None))
+                dL_dout_depth=grads_depth[v] if grads_depth is not None else None, accumulate_into=accumulate_into))
     for st in streams[:len(views)]:
         main.wait_stream(st)
     return res

@@ -261,3 +261,41 @@ def test_full_size_properties_c3():
     _, bw2 = util.run_ours(inp2)
     for k in ("dL_dmeans3D", "dL_dfeature", "dL_dopacity", "dL_dscales"):
         assert util.rel_l2(bw2[k], 2 * bw[k]) < 1e-5, k
+
+
+def test_multi_view_api_and_accumulate_mode():
+    """rasterize_views_raw (split forward, one stream per view) must reproduce the single-view entry point bit for bit,
+    and the accumulate mode must equal the sum of the per-view gradients (sum over views on one GPU ==
+    what the all-reduce produces across GPUs)."""
+    import torch
+    from manigaussian_b200 import rasterizer as R
+    from manigaussian_b200 import GaussianRasterizationSettings as S
+    from manigaussian_b200.parallel import PackedGradients
+    V, P, W, H, F = 3, 20000, 96, 80, 32
+    inps = [util.make_inputs(P=P, W=W, H=H, F=F, seed=77, view=v, num_views=V) for v in range(V)]
+    g = inps[0]["g"]
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    G = {k: t(g[k]) for k in ("means3D", "scales", "rotations", "opacities", "shs", "feature")}
+    e = torch.Tensor([])
+    views = [S(H, W, i["cam"]["tanfovx"], i["cam"]["tanfovy"], t(i["bg"]), 1.0, t(i["cam"]["viewmatrix"]), t(i["cam"]["projmatrix"]), 1,
+               t(i["cam"]["campos"]), False, False, True) for i in inps]
+    cts = [(t(i["ct"]["dL_dcolor"]), t(i["ct"]["dL_dfeature"])) for i in inps]
+    outs, sts = R.rasterize_views_raw(views, G["means3D"], e, G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0, e, G["shs"], 1, True)
+    pk = PackedGradients(P, F, 4, "cuda")
+    R.rasterize_views_backward_raw(views, outs, sts, [c[0] for c in cts], [c[1] for c in cts], G["means3D"], e, G["feature"], G["scales"],
+                                   G["rotations"], 1.0, e, G["shs"], 1, True, accumulate_into=pk.views)
+    torch.cuda.synchronize()
+    names = ("dL_dmeans2D", "dL_dcolors", "dL_dfeature", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations")
+    total = {}
+    for v, s in enumerate(views):
+        single = R.rasterize_gaussians_raw(s.bg, G["means3D"], e, G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0, e, s.viewmatrix,
+                                           s.projmatrix, s.tanfovx, s.tanfovy, H, W, G["shs"], 1, s.campos, False, False, True)
+        assert single[0] == outs[v][0]
+        assert torch.equal(single[1], outs[v][1]) and torch.equal(single[2], outs[v][2]) and torch.equal(single[3], outs[v][3])
+        gr = R.rasterize_gaussians_backward_raw(s.bg, G["means3D"], single[3], e, G["feature"], G["scales"], G["rotations"], 1.0, e, s.viewmatrix,
+                                                s.projmatrix, s.tanfovx, s.tanfovy, cts[v][0], cts[v][1], G["shs"], 1, s.campos, single[4],
+                                                single[0], single[5], single[6], False, True)
+        for n, x in zip(names, gr):
+            total[n] = x.double() if n not in total else total[n] + x.double()
+    for k, view in pk.views.items():
+        assert util.rel_l2(view.cpu().numpy(), total[k].reshape(view.shape).cpu().numpy()) < 1e-5, k
