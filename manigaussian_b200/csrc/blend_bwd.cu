@@ -23,9 +23,11 @@
 namespace mgs {
 
 constexpr int QCAP = 64;  // survivor queue capacity (power of two, >= 63)
+constexpr int PIX = 2;    // pixels interleaved per iteration of the pixel walk (instruction-level parallelism)
+constexpr int BWD_MIN_CTAS = PIX == 4 ? 8 : (PIX == 2 ? 12 : 16);
 
 template <int NQ, bool VEC>
-__global__ void __launch_bounds__(32, 16) blend_bwd_kernel(BlendArgs a)
+__global__ void __launch_bounds__(32, BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a)
 {
 	__shared__ __align__(128) InstRec s_rec[RING * REC_BATCH];
 	__shared__ __align__(16) float4 s_queue[QCAP * 2];   // survivors: {x,y,ca,cb}, {cc,op,pos,id}
@@ -123,68 +125,99 @@ __global__ void __launch_bounds__(32, 16) blend_bwd_kernel(BlendArgs a)
 		const float gx_ = r0.x, gy_ = r0.y, ca = r0.z, cb = r0.w, cc = r1.x, op = r1.y;
 		float dmx = 0.f, dmy = 0.f, dca = 0.f, dcb = 0.f, dcc = 0.f, dop = 0.f;
 
-		for (int p = 0; p < 32; p++) {
-			const float4 st = s_state[p];  // broadcast
-			const uint32_t ncp = __float_as_uint(st.z);
-			if (ncp == 0) continue;  // uniform: pixel outside the image or without contributors
-			const float pfx = (float)(bx0 + (p & 7)), pfy = (float)(by0 + (p >> 3));
-			const float dx = gx_ - pfx, dy = gy_ - pfy;
-			const float power = -0.5f * (ca * dx * dx + cc * dy * dy) - cb * dx * dy;
-			// ex2.approx-based exp (rel. error ~1e-6); the alpha >= 1/255 decision must agree with the forward's
-			// (which uses expf like the reference), so the rare borderline pairs are re-evaluated exactly
-			float G = __expf(power);
-			float alpha = min(ALPHA_MAX, op * G);
-			if (fabsf(alpha - ALPHA_MIN) < 2e-5f * ALPHA_MIN * 8.f) {
-				G = expf(power);
-				alpha = min(ALPHA_MAX, op * G);
+		// Two horizontally adjacent pixels per iteration: their scan chains (5 dependent shuffles each, twice) are
+		// independent, so interleaving them doubles the instruction-level parallelism of the latency-bound part.
+		for (int p = 0; p < 32; p += PIX) {
+			float4 st[PIX];
+			uint32_t ncp[PIX];
+			bool live_px = false;
+#pragma unroll
+			for (int u = 0; u < PIX; u++) {
+				st[u] = s_state[p + u];  // broadcast
+				ncp[u] = __float_as_uint(st[u].z);
+				live_px |= ncp[u] != 0;
 			}
-			const bool valid = have && (pos <= ncp) && (power <= 0.0f) && (alpha >= ALPHA_MIN);
-			if (!__any_sync(0xffffffffu, valid)) continue;
-			const float om = valid ? (1.f - alpha) : 1.f;
-			// inclusive product scan of (1 - alpha) over the chunk, lane 0 = farthest from the camera
-			float ip = om;
+			if (!live_px) continue;  // uniform: pixels outside the image or without contributors
+			float dx[PIX], dy[PIX], G[PIX], alpha[PIX];
+			bool valid[PIX];
+			bool any_valid = false;
+#pragma unroll
+			for (int u = 0; u < PIX; u++) {
+				const float pfx = (float)(bx0 + ((p + u) & 7)), pfy = (float)(by0 + ((p + u) >> 3));
+				dx[u] = gx_ - pfx; dy[u] = gy_ - pfy;
+				const float power = -0.5f * (ca * dx[u] * dx[u] + cc * dy[u] * dy[u]) - cb * dx[u] * dy[u];
+				// ex2.approx-based exp (rel. error ~1e-6); the alpha >= 1/255 decision must agree with the forward's
+				// (which uses expf like the reference), so the rare borderline pairs are re-evaluated exactly
+				G[u] = __expf(power);
+				alpha[u] = min(ALPHA_MAX, op * G[u]);
+				if (fabsf(alpha[u] - ALPHA_MIN) < 2e-5f * ALPHA_MIN * 8.f) {
+					G[u] = expf(power);
+					alpha[u] = min(ALPHA_MAX, op * G[u]);
+				}
+				valid[u] = have && (pos <= ncp[u]) && (power <= 0.0f) && (alpha[u] >= ALPHA_MIN);
+				any_valid |= valid[u];
+			}
+			if (!__any_sync(0xffffffffu, any_valid)) continue;
+			// inclusive product scans of (1 - alpha) over the chunk, lane 0 = farthest from the camera
+			float ip[PIX];
+#pragma unroll
+			for (int u = 0; u < PIX; u++) ip[u] = valid[u] ? (1.f - alpha[u]) : 1.f;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {
-				const float v = __shfl_up_sync(0xffffffffu, ip, o);
-				if (lane >= o) ip *= v;
+#pragma unroll
+				for (int u = 0; u < PIX; u++) {
+					const float v = __shfl_up_sync(0xffffffffu, ip[u], o);
+					if (lane >= o) ip[u] *= v;
+				}
 			}
-			const float Tk = __fdividef(st.x, ip);            // transmittance in front of this Gaussian
-			const float Tnew = __shfl_sync(0xffffffffu, Tk, 31);
-			const float wgt = valid ? alpha * Tk : 0.f;        // dchannel_dcolor
-
+			float Tk[PIX], wgt[PIX], w[PIX];
+#pragma unroll
+			for (int u = 0; u < PIX; u++) {
+				Tk[u] = __fdividef(st[u].x, ip[u]);            // transmittance in front of this Gaussian
+				wgt[u] = valid[u] ? alpha[u] * Tk[u] : 0.f;    // dchannel_dcolor
+				w[u] = 0.f;
+			}
 			// channel work: w = c_j . g_p ; dL/dc_j += wgt * g_p
-			float w = 0.f;
-			const float4* gp = s_g + p * NQ;
 #pragma unroll
 			for (int q = 0; q < NQ; q++) {
-				const float4 g = gp[q];
-				w += c[4 * q] * g.x; w += c[4 * q + 1] * g.y; w += c[4 * q + 2] * g.z; w += c[4 * q + 3] * g.w;
-				dch[4 * q] += wgt * g.x; dch[4 * q + 1] += wgt * g.y; dch[4 * q + 2] += wgt * g.z; dch[4 * q + 3] += wgt * g.w;
+#pragma unroll
+				for (int u = 0; u < PIX; u++) {
+					const float4 g = s_g[(p + u) * NQ + q];
+					w[u] += c[4 * q] * g.x; w[u] += c[4 * q + 1] * g.y; w[u] += c[4 * q + 2] * g.z; w[u] += c[4 * q + 3] * g.w;
+					dch[4 * q] += wgt[u] * g.x; dch[4 * q + 1] += wgt[u] * g.y; dch[4 * q + 2] += wgt[u] * g.z; dch[4 * q + 3] += wgt[u] * g.w;
+				}
 			}
 			// S_k = carried S + contributions of the lanes behind me in this chunk (exclusive prefix sum)
-			const float xk = wgt * w;
-			float is = xk;
+			float xk[PIX], is[PIX];
+#pragma unroll
+			for (int u = 0; u < PIX; u++) { xk[u] = wgt[u] * w[u]; is[u] = xk[u]; }
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1) {
-				const float v = __shfl_up_sync(0xffffffffu, is, o);
-				if (lane >= o) is += v;
+#pragma unroll
+				for (int u = 0; u < PIX; u++) {
+					const float v = __shfl_up_sync(0xffffffffu, is[u], o);
+					if (lane >= o) is[u] += v;
+				}
 			}
-			const float Sk = st.y + (is - xk);
-			const float Snew = st.y + __shfl_sync(0xffffffffu, is, 31);
-			if (lane == 0) s_state[p] = make_float4(Tnew, Snew, st.z, st.w);
-
-			if (valid) {
-				const float dL_dalpha = Tk * w - __fdividef(Sk + st.w, 1.f - alpha);
-				const float dL_dG = op * dL_dalpha;
-				const float gdx = G * dx, gdy = G * dy;
-				const float dG_ddelx = -gdx * ca - gdy * cb;
-				const float dG_ddely = -gdy * cc - gdx * cb;
-				dmx += dL_dG * dG_ddelx * ddelx_dx;
-				dmy += dL_dG * dG_ddely * ddely_dy;
-				dca += -0.5f * gdx * dx * dL_dG;
-				dcb += -0.5f * gdx * dy * dL_dG;
-				dcc += -0.5f * gdy * dy * dL_dG;
-				dop += G * dL_dalpha;
+#pragma unroll
+			for (int u = 0; u < PIX; u++) {
+				const float Sk = st[u].y + (is[u] - xk[u]);
+				const float Tnew = __shfl_sync(0xffffffffu, Tk[u], 31);
+				const float Snew = st[u].y + __shfl_sync(0xffffffffu, is[u], 31);
+				if (lane == 0) s_state[p + u] = make_float4(Tnew, Snew, st[u].z, st[u].w);
+				if (valid[u]) {
+					const float dL_dalpha = Tk[u] * w[u] - __fdividef(Sk + st[u].w, 1.f - alpha[u]);
+					const float dL_dG = op * dL_dalpha;
+					const float gdx = G[u] * dx[u], gdy = G[u] * dy[u];
+					const float dG_ddelx = -gdx * ca - gdy * cb;
+					const float dG_ddely = -gdy * cc - gdx * cb;
+					dmx += dL_dG * dG_ddelx * ddelx_dx;
+					dmy += dL_dG * dG_ddely * ddely_dy;
+					dca += -0.5f * gdx * dx[u] * dL_dG;
+					dcb += -0.5f * gdx * dy[u] * dL_dG;
+					dcc += -0.5f * gdy * dy[u] * dL_dG;
+					dop += G[u] * dL_dalpha;
+				}
 			}
 		}
 		__syncwarp();

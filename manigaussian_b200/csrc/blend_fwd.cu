@@ -115,19 +115,14 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 			const uint32_t pos0 = (uint32_t)(g * 32) + 1u;  // 1-based position of the chunk's first record in the tile list
 			int i = 0;
 			uint32_t mask = mask_cur;
-			while (mask) {
-				const int b = __ffs(mask) - 1;
-				mask &= mask - 1;
-				const float4* row = rows + i * NQ;
-				i++;
-				const float4 r0 = rec4[2 * b], r1 = rec4[2 * b + 1];  // {x, y, ca, cb}, {cc, op, ext, id}
-				const float dx = r0.x - pfx, dy = r0.y - pfy;
-				const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
-				if (done || power > 0.0f) continue;
-				const float alpha = min(ALPHA_MAX, r1.y * expf(power));
-				if (alpha < ALPHA_MIN) continue;
+			// Two survivors per iteration: their footprint evaluations (power, expf) are independent of the transmittance
+			// recurrence, so issuing both up front overlaps the second one's latency with the first one's channel FMAs.
+			auto blend_one = [&](int b, float power, float alpha_raw, const float4* row) {
+				if (done || power > 0.0f) return;
+				const float alpha = min(ALPHA_MAX, alpha_raw);
+				if (alpha < ALPHA_MIN) return;
 				const float test_T = T * (1 - alpha);
-				if (test_T < T_STOP) { done = true; continue; }
+				if (test_T < T_STOP) { done = true; return; }
 				const float w = alpha * T;
 #pragma unroll
 				for (int q = 0; q < NQ; q++) {
@@ -137,6 +132,23 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 				}
 				T = test_T;
 				last_contributor = pos0 + (uint32_t)b;
+			};
+			while (mask) {
+				const int b0 = __ffs(mask) - 1;
+				mask &= mask - 1;
+				const bool two = mask != 0;
+				const int b1 = two ? __ffs(mask) - 1 : b0;
+				if (two) mask &= mask - 1;
+				const float4 p0 = rec4[2 * b0], q0 = rec4[2 * b0 + 1];  // {x, y, ca, cb}, {cc, op, ext, id}
+				const float4 p1 = rec4[2 * b1], q1 = rec4[2 * b1 + 1];
+				const float dx0 = p0.x - pfx, dy0 = p0.y - pfy, dx1 = p1.x - pfx, dy1 = p1.y - pfy;
+				const float power0 = -0.5f * (p0.z * dx0 * dx0 + q0.x * dy0 * dy0) - p0.w * dx0 * dy0;
+				const float power1 = -0.5f * (p1.z * dx1 * dx1 + q1.x * dy1 * dy1) - p1.w * dx1 * dy1;
+				const float a0 = q0.y * expf(power0);
+				const float a1 = q1.y * expf(power1);
+				blend_one(b0, power0, a0, rows + i * NQ);
+				if (two) blend_one(b1, power1, a1, rows + (i + 1) * NQ);
+				i += two ? 2 : 1;
 			}
 		}
 		if (__all_sync(0xffffffffu, done)) {
