@@ -98,6 +98,8 @@ int mgs_forward(
  * *host_num_rendered (pinned host memory recommended) asynchronously; the caller may begin further views on other
  * streams, then synchronises each stream and calls mgs_forward_finish with the count to enqueue binning and the
  * blend.  mgs_forward == begin + stream sync + finish.  The geometry/image state of begin is passed back to finish.
+ * finish may itself be issued in two steps (stages 1 then 2) so that the short binning kernels of every view are
+ * enqueued before any view's long blend kernel.
  */
 int mgs_forward_begin(
 	mgs_alloc_fn geometry_alloc, void* geometry_user,
@@ -122,6 +124,7 @@ int mgs_forward_begin(
 	void* stream);
 int mgs_forward_finish(
 	mgs_alloc_fn binning_alloc, void* binning_user,
+	char* binning_state,   /* NULL unless stages == 2: the state allocated by an earlier stages == 1 call */
 	char* geometry_state,
 	char* image_state,
 	int P, int F,
@@ -133,6 +136,7 @@ int mgs_forward_finish(
 	float* out_color,
 	float* out_feature,
 	float* out_depth,
+	int stages,            /* bit 0: instance emission + per-tile order + records; bit 1: blend; 3 = both */
 	int debug,
 	void* stream);
 

@@ -44,7 +44,7 @@ def lib():
     L.mgs_forward_begin.argtypes = [ALLOC_FN, vp, ALLOC_FN, vp, i, i, i, i, i,
                                     vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, f, f, vp, vp, i, vp]
     L.mgs_forward_finish.restype = C.c_int
-    L.mgs_forward_finish.argtypes = [ALLOC_FN, vp, vp, vp, i, i, i, i, vp, vp, vp, i, vp, vp, vp, i, vp]
+    L.mgs_forward_finish.argtypes = [ALLOC_FN, vp, vp, vp, vp, i, i, i, i, vp, vp, vp, i, vp, vp, vp, i, i, vp]
     L.mgs_backward.restype = C.c_int
     L.mgs_backward.argtypes = [i, i, i, i, i,        # P D M F R
                                vp, i, i,             # background width height

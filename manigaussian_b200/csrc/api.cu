@@ -230,10 +230,12 @@ static int forward_phase1(
 }
 
 // ---- forward, phase 2: instance emission, per-tile order, records, blend ----
+// stages: bit 0 = binning (allocates the binning state through the callback), bit 1 = blend (uses `binning_state` when
+// given, else the one just allocated)
 static int forward_phase2(
-	mgs_alloc_fn binning_alloc, void* binning_user, char* geometry_state, char* image_state,
+	mgs_alloc_fn binning_alloc, void* binning_user, char* binning_state, char* geometry_state, char* image_state,
 	int P, int F, int width, int height, const float* background, const float* feature_precomp, const int* radii,
-	int num_rendered, float* out_color, float* out_feature, float* out_depth, int debug, cudaStream_t st)
+	int num_rendered, float* out_color, float* out_feature, float* out_depth, int stages, int debug, cudaStream_t st)
 {
 	if (num_rendered < 0) return fail(MGS_ERR_UNSUPPORTED, "more than 2^31-1 tile instances");
 	const int gx = ceil_div(width, TILE_X), gy = ceil_div(height, TILE_Y);
@@ -241,10 +243,15 @@ static int forward_phase2(
 	GeomState geom = GeomState::carve(geometry_state, (size_t)P);
 	ImageState img = ImageState::carve(image_state, N, T);
 
-	char* bchunk = binning_alloc(binning_user, mgs_binning_state_bytes(num_rendered));
-	if (!bchunk) return fail(MGS_ERR_ALLOC, "binning state allocation failed");
+	char* bchunk = binning_state;
+	if (stages & 1) {
+		if (!binning_alloc) return fail(MGS_ERR_INVALID_ARG, "binning allocator is required");
+		bchunk = binning_alloc(binning_user, mgs_binning_state_bytes(num_rendered));
+	}
+	if (!bchunk) return fail(MGS_ERR_ALLOC, "binning state missing");
 	BinState bin = BinState::carve(bchunk, (size_t)num_rendered);
 
+	if (stages & 1) {
 	{
 		StageTimer t_(ST_EMIT, st);
 		launch_emit_tiles(P, geom.order, geom.means2D, geom.point_offsets, radii, gx, gy, bin.tile_keys_unsorted, bin.point_list_unsorted, st);
@@ -264,6 +271,8 @@ static int forward_phase2(
 			img.ranges, bin.recs, st);
 	}
 	MGS_STAGE("ranges_pack");
+	}
+	if (!(stages & 2)) return num_rendered;
 
 	BlendArgs ba{};
 	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F; ba.nq = nq_for(F);
@@ -320,8 +329,8 @@ int mgs_forward(
 		&num_rendered, debug, st, &gstate, &istate);
 	if (rc < 0) return rc;
 	MGS_CUDA(cudaStreamSynchronize(st));  // the one host sync of the forward, as in the reference (rasterizer_impl.cu:284)
-	return forward_phase2(binning_alloc, binning_user, gstate, istate, P, F, width, height, background, feature_precomp, radii,
-		num_rendered, out_color, out_feature, out_depth, debug, st);
+	return forward_phase2(binning_alloc, binning_user, nullptr, gstate, istate, P, F, width, height, background, feature_precomp, radii,
+		num_rendered, out_color, out_feature, out_depth, 3, debug, st);
 }
 
 int mgs_forward_begin(
@@ -341,17 +350,17 @@ int mgs_forward_begin(
 }
 
 int mgs_forward_finish(
-	mgs_alloc_fn binning_alloc, void* binning_user, char* geometry_state, char* image_state,
+	mgs_alloc_fn binning_alloc, void* binning_user, char* binning_state, char* geometry_state, char* image_state,
 	int P, int F, int width, int height, const float* background, const float* feature_precomp, const int* radii,
-	int num_rendered, float* out_color, float* out_feature, float* out_depth, int debug, void* stream)
+	int num_rendered, float* out_color, float* out_feature, float* out_depth, int stages, int debug, void* stream)
 {
 	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-	if (!binning_alloc || !geometry_state || !image_state || !radii) return fail(MGS_ERR_INVALID_ARG, "required pointer is NULL");
+	if (!geometry_state || !image_state || !radii || !(stages & 3)) return fail(MGS_ERR_INVALID_ARG, "required argument is missing");
 	int rc = forward_check(P, width, height, F, background, feature_precomp, out_color, out_feature);
 	if (rc < 0) return rc;
 	if (P == 0) return fail(MGS_ERR_INVALID_ARG, "P must be > 0");
-	return forward_phase2(binning_alloc, binning_user, geometry_state, image_state, P, F, width, height, background, feature_precomp,
-		radii, num_rendered, out_color, out_feature, out_depth, debug, st);
+	return forward_phase2(binning_alloc, binning_user, binning_state, geometry_state, image_state, P, F, width, height, background,
+		feature_precomp, radii, num_rendered, out_color, out_feature, out_depth, stages, debug, st);
 }
 
 int mgs_backward(

@@ -401,24 +401,34 @@ def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scale
                     _ptr(cov3D_precomp), _ptr(vm), _ptr(pm), _ptr(cp), float(s.tanfovx), float(s.tanfovy), _ptr(radii),
                     counts.data_ptr() + 4 * v, int(bool(debug)), st.cuda_stream), "mgs_forward_begin")
                 pend.append((st, H, W, bg, vm, pm, cp, radii, ga, ia, ba))
-        outs = []
+        # binning of every view first (short kernels), then every view's blend (long kernels): a view's binning chain is
+        # never queued behind another view's blend
+        mid = []
         for v, (st, H, W, bg, vm, pm, cp, radii, ga, ia, ba) in enumerate(pend):
             st.synchronize()
             R = int(counts[v])
+            with torch.cuda.stream(st):
+                geom, img = ga.release(), ia.release()
+                _b.check(L.mgs_forward_finish(
+                    _ALLOC_CB, ba.key, None, _ptr(geom), _ptr(img), P, 0, W, H, _ptr(bg), None, _ptr(radii), R,
+                    _ptr(radii), None, None, 1, int(bool(debug)), st.cuda_stream), "mgs_forward_finish(binning)")
+                mid.append((R, geom, img, ba.release()))
+        outs = []
+        for v, (st, H, W, bg, vm, pm, cp, radii, ga, ia, ba) in enumerate(pend):
+            R, geom, img, binb = mid[v]
             with torch.cuda.stream(st):
                 out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
                 out_feature = torch.empty((F, H, W), dtype=torch.float32, device=dev) if include_feature else \
                     torch.zeros((1,), dtype=torch.float32, device=dev)
                 out_depth = torch.empty((H, W), dtype=torch.float32, device=dev) if return_depth else None
-                geom, img = ga.release(), ia.release()
                 _b.check(L.mgs_forward_finish(
-                    _ALLOC_CB, ba.key, _ptr(geom), _ptr(img), P, F, W, H, _ptr(bg), _ptr(language_feature) if F else None,
-                    _ptr(radii), R, _ptr(out_color), _ptr(out_feature) if F else None, _ptr(out_depth), int(bool(debug)),
-                    st.cuda_stream), "mgs_forward_finish")
-                ret = (R, out_color, out_feature, radii, geom, ba.release(), img)
+                    _ALLOC_CB, None, _ptr(binb), _ptr(geom), _ptr(img), P, F, W, H, _ptr(bg), _ptr(language_feature) if F else None,
+                    _ptr(radii), R, _ptr(out_color), _ptr(out_feature) if F else None, _ptr(out_depth), 2, int(bool(debug)),
+                    st.cuda_stream), "mgs_forward_finish(blend)")
+                ret = (R, out_color, out_feature, radii, geom, binb, img)
                 outs.append(ret + (out_depth,) if return_depth else ret)
                 if after_view is not None:
-                    after_view(v, outs[-1])  # still inside view v's stream context: e.g. enqueue its backward right away
+                    after_view(v, outs[-1])  # still inside view v's stream context
     return outs, streams
 
 
