@@ -405,31 +405,37 @@ def nbytes(d):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_baseline(wl, budget_gaussians=100_000):
-    """Oracle port (oracle/gs_oracle.c, all host threads) on a bounded sample of the workload: the first
-    `budget_gaussians` Gaussians of the cloud (same per-Gaussian footprint), view 0, fwd+bwd."""
+def cpu_baseline(wl, target_s=12.0):
+    """Oracle port (oracle/gs_oracle.c, OpenMP, all host threads) on a bounded sample of the workload.  A probe on the
+    first 100k Gaussians of view 0 sizes the sample: the full cloud, as many of the workload's views as fit in about
+    `target_s` seconds of CPU work (at least one)."""
     from manigaussian_b200 import scenes
     from oracle import gs_oracle as O
-    P, W, H, F = wl["P"], wl["W"], wl["H"], wl["F"]
-    Ps = min(P, budget_gaussians)
-    g = scenes.make_gaussians(P, F=F, sh_degree=SH_DEGREE, seed=1234)
-    g = {k: (v[:Ps] if isinstance(v, np.ndarray) else v) for k, v in g.items()}
-    cam = scenes.make_camera(W, H, 0, wl["views"])
-    ct = scenes.make_cotangents(W, H, F, seed=100)
+    P, W, H, F, V = wl["P"], wl["W"], wl["H"], wl["F"], wl["views"]
+    gfull = scenes.make_gaussians(P, F=F, sh_degree=SH_DEGREE, seed=1234)
     bg = np.zeros(3, np.float32)
-    kw = dict(scales=g["scales"], rotations=g["rotations"], shs=g["shs"], sh_degree=SH_DEGREE, feature=g["feature"])
     cores = O.max_threads()
-    best = None
-    for _ in range(2):
+
+    def run(n, view):
+        g = {k: (v[:n] if isinstance(v, np.ndarray) else v) for k, v in gfull.items()}
+        cam = scenes.make_camera(W, H, view, V)
+        ct = scenes.make_cotangents(W, H, F, seed=100 + view)
+        kw = dict(scales=g["scales"], rotations=g["rotations"], shs=g["shs"], sh_degree=SH_DEGREE, feature=g["feature"])
         t0 = time.perf_counter()
         fw = O.forward(g["means3D"], g["opacities"], cam["viewmatrix"], cam["projmatrix"], cam["campos"], W, H, cam["tanfovx"],
                        cam["tanfovy"], bg, **kw)
         O.backward(fw, ct["dL_dcolor"], ct["dL_dfeature"], g["means3D"], cam["viewmatrix"], cam["projmatrix"], cam["campos"],
                    cam["tanfovx"], cam["tanfovy"], bg, **kw)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return {"value": Ps / best, "unit": "Gaussians/s", "cores": cores, "kind": "port",
-            "sample": f"first {Ps} of {P} Gaussians, view 0 of {wl['views']}, {W}x{H}, F={F}, fwd+bwd, best of 2 ({best:.2f} s)"}, best
+        return time.perf_counter() - t0
+
+    probe_n = min(P, 100_000)
+    probe = min(run(probe_n, 0), run(probe_n, 0))
+    est_view = probe * P / probe_n * 1.3  # deeper per-pixel lists at full density
+    nviews = int(max(1, min(V, target_s // max(est_view, 1e-3))))
+    total = sum(run(P, v) for v in range(nviews))
+    return {"value": P * nviews / total, "unit": "Gaussians/s", "cores": cores, "kind": "port",
+            "sample": f"all {P} Gaussians, views 0..{nviews - 1} of {V}, {W}x{H}, F={F}, fwd+bwd, {total:.1f} s of CPU work "
+                      f"(probe: {probe_n} Gaussians in {probe:.2f} s)"}, total
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -509,7 +515,7 @@ def main():
         time.sleep(0.3)
     if a.impl == "ours":
         from manigaussian_b200 import _binding
-        _binding.profile_enable(not a.no_stage_timing)
+        _binding.profile_enable(False)
     t_settle, n_settle = time.perf_counter(), 0
     while time.perf_counter() - t_settle < a.settle:
         Rtot = run_step(impl, G, C, T, flat, acc, None, streams)  # no collective: ranks settle for a time, not a count
@@ -531,12 +537,20 @@ def main():
     e1.record()
     barrier()
     t_stop = time.perf_counter()
-    cfg["host_step_ms"] = [round((b_ - a_) * 1e3, 2) for a_, b_ in zip([t_start] + step_marks[:-1], step_marks)]
+    hs = sorted((b_ - a_) * 1e3 for a_, b_ in zip([t_start] + step_marks[:-1], step_marks))
+    cfg["host_step_ms"] = {"min": round(hs[0], 3), "median": round(hs[len(hs) // 2], 3), "max": round(hs[-1], 3)}
     clocks = sampler.stop(t_start, t_stop)
     ms = e0.elapsed_time(e1)
     cfg["wall_ms_per_step"] = (t_stop - t_start) * 1e3 / a.steps
     stages = None
-    if a.impl == "ours":
+    if a.impl == "ours" and not a.no_stage_timing:
+        # per-stage CUDA-event durations for the roofline leg: a separate short pass with views enqueued one after the
+        # other on ONE stream, so that each duration is that kernel alone (in the timed region above views overlap)
+        _binding.profile_read()
+        _binding.profile_enable(True)
+        for _ in range(3):
+            run_step(impl, G, C, T, flat, acc, None, None)
+        torch.cuda.synchronize()
         stages = _binding.profile_read()
         _binding.profile_enable(False)
     tmax = torch.tensor([ms], device="cuda")
@@ -611,8 +625,13 @@ def main():
             "ranges_pack": R_view * (8 + 32) + 32 * R_view, "scan": 8 * P,
         }.get(dom, 0)
         ach = alg / (per[dom] * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(a.workload, {}).get(dom)
+        except Exception:
+            pass
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                           "traffic": None, "alg_bytes_per_launch": alg, "ms_per_launch": per[dom], "peak_source": peak_src,
+                           "traffic": traffic, "alg_bytes_per_launch": alg, "ms_per_launch": per[dom], "peak_source": peak_src,
                            "note": "blend kernels are FP32-issue bound, not HBM bound (DESIGN.md)"}
     else:
         if stages is None:

@@ -299,3 +299,41 @@ def test_multi_view_api_and_accumulate_mode():
             total[n] = x.double() if n not in total else total[n] + x.double()
     for k, view in pk.views.items():
         assert util.rel_l2(view.cpu().numpy(), total[k].reshape(view.shape).cpu().numpy()) < 1e-5, k
+
+
+def test_dynamic_path_gradients_reach_deformation_offsets():
+    """BASELINE.json configs[3] / SURVEY.md 3.5: the 'dyna' render uses mu + d_mu, normalize(r + d_r) and (extension)
+    s + d_s (models_embed.py:297-304); the offsets' gradients are the rasterizer's dL/dmeans3D, dL/drotations chained
+    through normalize, and dL/dscales.  Checked against the oracle with the chain rule done in float64 on the CPU."""
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    inp = util.make_inputs(P=6000, W=96, H=96, F=32, seed=91, scale0=0.012)  # moderate splats: see ORACLE_GRAD_TOL
+    cam, g, ct = inp["cam"], inp["g"], inp["ct"]
+    rng = np.random.default_rng(5)
+    d_mu = rng.normal(0, 0.01, g["means3D"].shape).astype(np.float32)
+    d_r = rng.normal(0, 0.05, g["rotations"].shape).astype(np.float32)
+    d_s = (rng.normal(0, 0.1, g["scales"].shape) * g["scales"]).astype(np.float32)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    tmu, tr, ts = t(d_mu).requires_grad_(True), t(d_r).requires_grad_(True), t(d_s).requires_grad_(True)
+    means = t(g["means3D"]) + tmu
+    rots = torch.nn.functional.normalize(t(g["rotations"]) + tr, dim=-1)
+    scales = t(g["scales"]) + ts
+    st = GaussianRasterizationSettings(96, 96, cam["tanfovx"], cam["tanfovy"], t(inp["bg"]), 1.0, t(cam["viewmatrix"]),
+                                       t(cam["projmatrix"]), 1, t(cam["campos"]), False, False, True)
+    img, emb, _ = GaussianRasterizer(st)(means3D=means, means2D=torch.zeros_like(means), opacities=t(g["opacities"]), shs=t(g["shs"]),
+                                         language_feature_precomp=t(g["feature"]), scales=scales, rotations=rots)
+    ((img * t(ct["dL_dcolor"])).sum() + (emb * t(ct["dL_dfeature"])).sum()).backward()
+    # oracle on the deformed cloud
+    g2 = dict(g)
+    q = g["rotations"].astype(np.float64) + d_r
+    g2["means3D"] = (g["means3D"] + d_mu).astype(np.float32)
+    g2["rotations"] = rots.detach().cpu().numpy()
+    g2["scales"] = (g["scales"] + d_s).astype(np.float32)
+    inp2 = dict(inp)
+    inp2["g"] = g2
+    _, bw = util.run_oracle(inp2)
+    qt = torch.from_numpy(q).requires_grad_(True)
+    torch.nn.functional.normalize(qt, dim=-1).backward(torch.from_numpy(bw["dL_drotations"].astype(np.float64)))
+    assert util.rel_l2(tmu.grad.cpu().numpy(), bw["dL_dmeans3D"]) < TOL
+    assert util.rel_l2(ts.grad.cpu().numpy(), bw["dL_dscales"]) < TOL
+    assert util.rel_l2(tr.grad.cpu().numpy(), qt.grad.numpy()) < TOL
