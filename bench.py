@@ -432,9 +432,14 @@ def cpu_baseline(wl, target_s=12.0):
     probe = min(run(probe_n, 0), run(probe_n, 0))
     est_view = probe * P / probe_n * 1.3  # deeper per-pixel lists at full density
     nviews = int(max(1, min(V, target_s // max(est_view, 1e-3))))
-    total = sum(run(P, v) for v in range(nviews))
+    total, reps = 0.0, 0
+    while reps < 4 and total < 0.8 * target_s:
+        total += sum(run(P, v) for v in range(nviews))
+        reps += 1
+    nviews *= reps
     return {"value": P * nviews / total, "unit": "Gaussians/s", "cores": cores, "kind": "port",
-            "sample": f"all {P} Gaussians, views 0..{nviews - 1} of {V}, {W}x{H}, F={F}, fwd+bwd, {total:.1f} s of CPU work "
+            "sample": f"all {P} Gaussians, {nviews} view renders (views of the workload, repeated {reps}x), {W}x{H}, F={F}, fwd+bwd, "
+                      f"{total:.1f} s of CPU work "
                       f"(probe: {probe_n} Gaussians in {probe:.2f} s)"}, total
 
 
@@ -608,7 +613,8 @@ def main():
         per = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
         cfg["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
         hand = ("project_fwd", "emit_tiles", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd")
-        out["gpu_launches"] = int(sum(stages[k][1] for k in hand if k in stages))
+        # hand-written kernels launched inside the timed region: six per view and step
+        out["gpu_launches"] = len(hand) * V * a.steps
         cfg["library_launches_cub"] = "depth sort + scan + tile sort (CUB) per view, not counted in gpu_launches"
         dom = max(per, key=per.get)
         if per[dom] <= 0:

@@ -331,9 +331,15 @@ def test_dynamic_path_gradients_reach_deformation_offsets():
     g2["scales"] = (g["scales"] + d_s).astype(np.float32)
     inp2 = dict(inp)
     inp2["g"] = g2
-    _, bw = util.run_oracle(inp2)
+    # expected gradients of the deformed cloud: the compiled reference when its build travelled (1e-4 bar), else the CPU
+    # oracle (covariance-derived tensors then carry the gcc-vs-nvcc fp32 evaluation-order noise, see ORACLE_GRAD_TOL)
+    _, bw = util.run_reference(inp2)
+    tol_cov = TOL
+    if bw is None:
+        _, bw = util.run_oracle(inp2)
+        tol_cov = 1e-3
     qt = torch.from_numpy(q).requires_grad_(True)
     torch.nn.functional.normalize(qt, dim=-1).backward(torch.from_numpy(bw["dL_drotations"].astype(np.float64)))
-    assert util.rel_l2(tmu.grad.cpu().numpy(), bw["dL_dmeans3D"]) < TOL
-    assert util.rel_l2(ts.grad.cpu().numpy(), bw["dL_dscales"]) < TOL
-    assert util.rel_l2(tr.grad.cpu().numpy(), qt.grad.numpy()) < TOL
+    assert util.rel_l2(tmu.grad.cpu().numpy(), bw["dL_dmeans3D"]) < tol_cov
+    assert util.rel_l2(ts.grad.cpu().numpy(), bw["dL_dscales"]) < tol_cov
+    assert util.rel_l2(tr.grad.cpu().numpy(), qt.grad.numpy()) < tol_cov
