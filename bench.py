@@ -35,6 +35,8 @@ WORKLOADS = {
     "c1": dict(P=50_000, views=1, W=128, H=128, F=0, depth=False, desc="50k Gaussians, 1 view 128x128, RGB-only"),
     "c2": dict(P=200_000, views=1, W=256, H=256, F=0, depth=True, desc="200k Gaussians, 1 view 256x256, RGB+depth"),
     "c3": dict(P=500_000, views=4, W=256, H=256, F=32, depth=False, desc="500k Gaussians, 4 views 256x256, RGB+32 feat"),
+    "c4": dict(P=500_000, views=4, W=256, H=256, F=32, depth=False, dyna=True,
+               desc="500k Gaussians + deformation offsets (dyna path): 4 views current frame + 4 views next frame, 256x256, RGB+32 feat"),
     "c5": dict(P=1_000_000, views=1, W=256, H=256, F=32, depth=False, desc="1M Gaussians, 1 view/GPU 256x256, RGB+32 feat"),
     "mg": dict(P=16_384, views=1, W=128, H=128, F=3, depth=False, desc="ManiGaussian's real call: 16384 Gaussians, 128x128, F=3"),
 }
@@ -284,7 +286,8 @@ def run_step(impl, G, C, T, flat, acc, dist=None, streams=None):
 
 
 # ------------------------------------------------------------------------------------------------ e2e (public API)
-def make_e2e(impl_name, wl, torch):
+def make_render(impl_name, wl, torch):
+    """render(st, **kw) -> (color, feature, radii[, depth]) through the autograd API of the chosen implementation."""
     P, F = wl["P"], wl["F"]
     if impl_name == "ours":
         from manigaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer
@@ -336,9 +339,15 @@ def make_e2e(impl_name, wl, torch):
                 return color, lf[:F], radii, lf[F]
             return color, lf[:F], radii
 
+    return render, GaussianRasterizationSettings
+
+
+def make_e2e(impl_name, wl, torch):
+    P, F = wl["P"], wl["F"]
+    render, GaussianRasterizationSettings = make_render(impl_name, wl, torch)
     copy_stream = torch.cuda.Stream()
     V = wl["views"]
-    view_streams = [torch.cuda.Stream() for _ in range(V)] if (impl_name == "ours" and V > 1) else None
+    view_streams = None  # ours: render_views owns its per-view streams; the reference launches on the legacy default stream
 
     def upload(Gh, Ch, Th):
         """H2D copy of ONE step's inputs (pinned host -> device) on a copy stream, so that step i+1's inputs travel while
@@ -363,28 +372,33 @@ def make_e2e(impl_name, wl, torch):
                     for u in users:
                         v.record_stream(u)
         G = {k: (v.requires_grad_(True) if v is not None and v.numel() else v) for k, v in G.items()}
+        if impl_name == "ours":
+            # the public multi-view call: ONE autograd node for all views, gradients summed on the device
+            from manigaussian_b200.gaussian_renderer import render_views
+            views = [GaussianRasterizationSettings(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], cam["bg"], 1.0, cam["viewmatrix"],
+                                                   cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, F > 0) for cam in C]
+            o = render_views(views, G["means3D"], G["rotations"], G["scales"], G["opacities"], features_color=G["shs"],
+                             features_language=G["feature"] if F else None, return_depth=wl["depth"], normalize_feature=False)
+            loss = (o["render"] * torch.stack([ct["dL_dcolor"] for ct in T])).sum()
+            if F:
+                loss = loss + (o["render_embed"] * torch.stack([ct["dL_dfeature"] for ct in T])).sum()
+            if wl["depth"]:
+                loss = loss + (o["depth"] * torch.stack([ct["dL_ddepth"] for ct in T])).sum()
+            loss.backward()
+            return float(loss.item())
         losses = []
-        for i, (cam, ct) in enumerate(zip(C, T)):
-            s = view_streams[i] if view_streams else None
-            if s is not None:
-                s.wait_stream(main)
-            with torch.cuda.stream(s if s is not None else main):
-                st = GaussianRasterizationSettings(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], cam["bg"], 1.0,
-                                                   cam["viewmatrix"], cam["projmatrix"], SH_DEGREE, cam["campos"], False, False,
-                                                   F > 0 or impl_name != "ours")
-                kw = dict(means3D=G["means3D"], means2D=torch.zeros_like(G["means3D"], requires_grad=True),
-                          opacities=G["opacities"], shs=G["shs"], language_feature_precomp=G["feature"] if F else None,
-                          scales=G["scales"], rotations=G["rotations"])
-                out = render(st, **kw)
-                lv = (out[0] * ct["dL_dcolor"]).sum()
-                if F:
-                    lv = lv + (out[1] * ct["dL_dfeature"]).sum()
-                if wl["depth"]:
-                    lv = lv + (out[3] * ct["dL_ddepth"]).sum()
+        for cam, ct in zip(C, T):
+            st = GaussianRasterizationSettings(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], cam["bg"], 1.0,
+                                               cam["viewmatrix"], cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, True)
+            out = render(st, means3D=G["means3D"], means2D=torch.zeros_like(G["means3D"], requires_grad=True),
+                         opacities=G["opacities"], shs=G["shs"], language_feature_precomp=G["feature"] if F else None,
+                         scales=G["scales"], rotations=G["rotations"])
+            lv = (out[0] * ct["dL_dcolor"]).sum()
+            if F:
+                lv = lv + (out[1] * ct["dL_dfeature"]).sum()
+            if wl["depth"]:
+                lv = lv + (out[3] * ct["dL_ddepth"]).sum()
             losses.append(lv)
-        if view_streams:
-            for s in view_streams:
-                main.wait_stream(s)
         loss = losses[0]
         for lv in losses[1:]:
             loss = loss + lv
@@ -398,6 +412,158 @@ def make_e2e(impl_name, wl, torch):
         return compute(dev)
 
     return step
+
+
+# ------------------------------------------------------------------------------------------------ dyna path (c4)
+def dyna_host_inputs(g, seed=4321):
+    """Raw network outputs whose activations reproduce the synthetic cloud: xyz + xyz_maps, log-scales,
+    opacity logits, un-normalised quaternions/features, and the deformation field's offsets for the next frame."""
+    rng = np.random.default_rng(seed)
+    P = g["means3D"].shape[0]
+    f32 = lambda x: np.ascontiguousarray(x, np.float32)
+    xyz_maps = rng.normal(0, 0.01, (P, 3))
+    return dict(xyz=f32(g["means3D"] - xyz_maps), xyz_maps=f32(xyz_maps), rot_maps=f32(g["rotations"] * rng.uniform(0.5, 2.0, (P, 1))),
+                scale_maps=f32(np.log(g["scales"])), opacity_maps=f32(np.log(g["opacities"] / (1 - g["opacities"]))), sh=f32(g["shs"]),
+                feature_maps=f32(g["feature"] * rng.uniform(0.5, 2.0, (P, 1))), next_xyz=f32(rng.normal(0, 0.01, (P, 3))),
+                next_rot=f32(rng.normal(0, 0.05, (P, 4))), next_scale=f32(rng.normal(0, 0.1, (P, 3)) * g["scales"]))
+
+
+def make_dyna_step(impl_name, wl, torch):
+    """step(raw, C, T2) -> loss tensor: activations -> V current-frame views + V next-frame views -> backward to every raw
+    map and offset (models_embed.py:245-252, 297-304; neural_rendering.py:383-402 for both frames)."""
+    F, V = wl["F"], wl["views"]
+    if impl_name == "ours":
+        from manigaussian_b200 import GaussianRasterizationSettings
+        from manigaussian_b200.gaussian_params import activate_gaussians
+        from manigaussian_b200.gaussian_renderer import render_views
+
+        def step(raw, C, T2):
+            L = {k: (v.detach().requires_grad_(True) if k != "xyz" else v) for k, v in raw.items()}
+            views = [GaussianRasterizationSettings(c["H"], c["W"], c["tanfovx"], c["tanfovy"], c["bg"], 1.0, c["viewmatrix"],
+                                                   c["projmatrix"], SH_DEGREE, c["campos"], False, False, True) for c in C]
+            cur = activate_gaussians(L["xyz"], L["rot_maps"], L["scale_maps"], L["opacity_maps"], L["feature_maps"], d_means=L["xyz_maps"])
+            nxt = activate_gaussians(cur[0].detach(), cur[1].detach(), cur[2].detach(), cur[3].detach(), None, d_means=L["next_xyz"],
+                                     d_rotations=L["next_rot"], d_scales=L["next_scale"], scale_activation=None, opacity_activation=None)
+            oc = render_views(views, cur[0], cur[1], cur[2], cur[3], features_color=L["sh"], features_language=cur[4], normalize_feature=False)
+            on = render_views(views, nxt[0], nxt[1], nxt[2], nxt[3], features_color=L["sh"].detach(),
+                              features_language=cur[4].detach(), normalize_feature=False)
+            loss = (oc["render"] * T2["color"][0]).sum() + (oc["render_embed"] * T2["feature"][0]).sum() + \
+                   (on["render"] * T2["color"][1]).sum() + (on["render_embed"] * T2["feature"][1]).sum()
+            loss.backward()
+            return loss, L
+    else:
+        render, GaussianRasterizationSettings = make_render(impl_name, wl, torch)
+
+        def step(raw, C, T2):
+            L = {k: (v.detach().requires_grad_(True) if k != "xyz" else v) for k, v in raw.items()}
+            scales = torch.clamp_max(torch.exp(L["scale_maps"]), 0.05)
+            means = L["xyz"] + L["xyz_maps"]
+            rots = torch.nn.functional.normalize(L["rot_maps"], dim=-1)
+            opac = torch.sigmoid(L["opacity_maps"])
+            n_means = means.detach() + L["next_xyz"]
+            n_rots = torch.nn.functional.normalize(rots.detach() + L["next_rot"], dim=-1)
+            n_scales = scales.detach() + L["next_scale"]
+            loss = 0
+            for v, c in enumerate(C):
+                st = GaussianRasterizationSettings(c["H"], c["W"], c["tanfovx"], c["tanfovy"], c["bg"], 1.0, c["viewmatrix"],
+                                                   c["projmatrix"], SH_DEGREE, c["campos"], False, False, True)
+                for fr, (m, r, s_, o, sh, f) in enumerate(((means, rots, scales, opac, L["sh"], L["feature_maps"]),
+                                                            (n_means, n_rots, n_scales, opac.detach(), L["sh"].detach(),
+                                                             L["feature_maps"].detach()))):
+                    fn = f / (f.norm(dim=-1, keepdim=True) + 1e-12)   # the reference normalises inside every render()
+                    out = render(st, means3D=m, means2D=torch.zeros_like(m, requires_grad=True), opacities=o, shs=sh,
+                                 language_feature_precomp=fn, scales=s_, rotations=r)
+                    loss = loss + (out[0] * T2["color"][fr][v]).sum() + (out[1] * T2["feature"][fr][v]).sum()
+            loss.backward()
+            return loss, L
+    return step
+
+
+def main_dyna(a, wl, base, cfg, torch, rank, world):
+    """c4: device-timed value and host-buffer e2e of the dyna step, same JSON contract."""
+    P, V, W, H, F = wl["P"], wl["views"], wl["W"], wl["H"], wl["F"]
+    g, cams, _ = host_inputs(wl, rank, world)
+    raw_h = dyna_host_inputs(g)
+    rng = np.random.default_rng(77)
+    T2_h = {"color": rng.standard_normal((2, V, 3, H, W)).astype(np.float32), "feature": rng.standard_normal((2, V, F, H, W)).astype(np.float32)}
+    pin = lambda x: torch.from_numpy(x).pin_memory()
+    raw_p, T2_p = {k: pin(v) for k, v in raw_h.items()}, {k: pin(v) for k, v in T2_h.items()}
+    _, C, _ = to_device(g, cams, [], torch)
+    raw = {k: v.cuda() for k, v in raw_p.items()}
+    T2 = {k: v.cuda() for k, v in T2_p.items()}
+    step = make_dyna_step(a.impl, wl, torch)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)), period=0.025)
+    if not a.no_clocks:
+        sampler.start()
+        time.sleep(0.3)
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < a.settle:
+        step(raw, C, T2)
+        torch.cuda.synchronize()
+    for _ in range(a.warmup):
+        step(raw, C, T2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        loss, L = step(raw, C, T2)
+    e1.record()
+    torch.cuda.synchronize()
+    t_stop = time.perf_counter()
+    clocks = sampler.stop(t_start, t_stop)
+    ms_step = e0.elapsed_time(e1) / a.steps
+    units = P * 2 * V
+    out = dict(base, value=units / (ms_step * 1e-3), ms_per_step=ms_step, clocks=clocks)
+    cfg.update(gaussian_views_per_step=2 * V, loss=float(loss.item()),
+               grads_checked={k: bool(torch.isfinite(v.grad).all().item()) for k, v in L.items() if v.requires_grad},
+               l2="no flush: per-step working set exceeds the 126 MB L2")
+    out["config"] = cfg
+    if not a.no_e2e:
+        copy_stream = torch.cuda.Stream()
+
+        def upload():
+            with torch.cuda.stream(copy_stream):
+                d = ({k: v.cuda(non_blocking=True) for k, v in raw_p.items()}, {k: v.cuda(non_blocking=True) for k, v in T2_p.items()})
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return d + (ev,)
+
+        def e2e_step(state):
+            dev = state.get("dev") or upload()
+            state["dev"] = upload()
+            r, t2, ev = dev
+            torch.cuda.current_stream().wait_event(ev)
+            for d in (r, t2):
+                for v in d.values():
+                    v.record_stream(torch.cuda.current_stream())
+            return float(step(r, C, t2)[0].item())
+        state = {}
+        for _ in range(3):
+            e2e_step(state)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step(state)
+        torch.cuda.synchronize()
+        te = (time.perf_counter() - t0) / a.steps
+        out["e2e"] = {"value": units / te, "unit": "Gaussians/s", "ms_per_step": te * 1e3, "d2h_bytes_per_step": 4,
+                      "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in raw_p.values()) + sum(v.numel() * 4 for v in T2_p.values()))}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    out["gpu_launches"] = (6 * 2 * V + 4) * a.steps if a.impl == "ours" else 0
+    out["roofline"] = {"bound": "hbm", "kernel": "whole pipeline", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                       "traffic": None, "note": "per-kernel roofline is reported by the c3 line (same rasterizer kernels)"}
+    if a.gpus == 1 and not a.no_cpu_baseline:
+        cb, _ = cpu_baseline(wl)
+        cb["sample"] += " [rasterizer of one frame; activations not included]"
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    return 0
 
 
 def nbytes(d):
@@ -496,6 +662,10 @@ def main():
         import datetime
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
         dist = dist_mod
+    if wl.get("dyna"):
+        if world > 1:
+            raise SystemExit("workload c4 is a single-GPU configuration (BASELINE.json configs[3])")
+        return main_dyna(a, wl, base, cfg, torch, rank, world)
     P, V, W, H, F = wl["P"], wl["views"], wl["W"], wl["H"], wl["F"]
     M = (SH_DEGREE + 1) ** 2
     g, cams, cts = host_inputs(wl, rank, world)
@@ -514,7 +684,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period=0.025)
     if not a.no_clocks:
         sampler.start()
         time.sleep(0.3)
@@ -585,7 +755,8 @@ def main():
                "h2d_bytes_per_step": int(nbytes(Gh) + sum(nbytes(c) for c in Ch) + sum(nbytes(t) for t in Th)),
                "d2h_bytes_per_step": 4, "ms_per_step": float(te.item()) * 1e3,
                "note": "wall clock around K steps; every step copies all its inputs pinned-host->device (prefetched one step ahead on a "
-                       "copy stream), runs the autograd module API per view, and reads loss.item() back"}
+                       "copy stream), runs the public autograd API (ours: manigaussian_b200.gaussian_renderer.render_views, one node "
+                       "for all views; reference: its autograd Function per view), and reads loss.item() back"}
 
     if rank != 0:
         if dist is not None:

@@ -23,7 +23,8 @@
  *  - outputs are fully overwritten: callers need not zero-initialise them.
  *
  * All functions return >= 0 on success and a negative MGS_ERR_* code on failure; mgs_last_error() returns a
- * thread-local description.  No global state, no handles; re-entrant like the reference.
+ * thread-local description.  No handles; re-entrant like the reference.  The only process-wide state is a cache of
+ * sort/scan scratch sizes and the opt-in stage timers of mgs_profile_*.
  */
 #ifndef MGS_RASTERIZER_H
 #define MGS_RASTERIZER_H
@@ -196,6 +197,34 @@ int mgs_backward(
  * present: uint8 [P], 1 where view-space z > 0.2. */
 int mgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
 	uint8_t* present, void* stream);
+
+/*
+ * View-independent per-Gaussian pre-ops, one fused kernel per direction ("next" row f2 of the scope table).
+ * Replaces the elementwise PyTorch chain ManiGaussian applies to the rasterizer's inputs once per step:
+ *   means  = means + d_means                                   (agents/manigaussian_bc/models_embed.py:248, :299)
+ *   rot    = normalize(rot + d_rot), x / max(||x||, 1e-12)      (models_embed.py:250, :301)
+ *   scales = min(exp(scales + d_scales), scale_max)            (models_embed.py:245-246; scale_mode 1; 0 = identity)
+ *   opac   = sigmoid(opac)                                     (models_embed.py:252; opacity_mode 1; 0 = identity)
+ *   feat   = feat / (||feat|| + 1e-12)                         (agents/manigaussian_bc/gaussian_renderer/__init__.py:66-68)
+ * Every d_* offset is optional (NULL); every output is optional (NULL skips the field).  Outputs must not alias inputs.
+ * F is unrestricted here (>= 0).  mgs_activate_backward takes dL/d(activated arrays) -- typically the sums over all
+ * views that mgs_backward accumulated -- recomputes the forward from the raw inputs and writes dL/d(raw) and, where
+ * asked, the same values as dL/d(offset).  NULL g_* skips a field; NULL outputs are not written.
+ */
+int mgs_activate(int P, int F,
+	const float* means, const float* d_means, const float* rot, const float* d_rot,
+	const float* scales, const float* d_scales, const float* opac, const float* feature,
+	int scale_mode, float scale_max, int opacity_mode, int rot_normalize, int feature_normalize,
+	float* out_means, float* out_rot, float* out_scales, float* out_opac, float* out_feature,
+	void* stream);
+int mgs_activate_backward(int P, int F,
+	const float* means, const float* d_means, const float* rot, const float* d_rot,
+	const float* scales, const float* d_scales, const float* opac, const float* feature,
+	int scale_mode, float scale_max, int opacity_mode, int rot_normalize, int feature_normalize,
+	const float* g_means, const float* g_rot, const float* g_scales, const float* g_opac, const float* g_feature,
+	float* dL_dmeans, float* dL_dd_means, float* dL_drot, float* dL_dd_rot,
+	float* dL_dscales, float* dL_dd_scales, float* dL_dopac, float* dL_dfeature,
+	void* stream);
 
 /*
  * Test/diagnostic access to the opaque state (used by the parity tests to compare stage by stage with the

@@ -65,7 +65,16 @@ def lib():
     L.mgs_profile_stage_name.restype = C.c_char_p
     L.mgs_profile_stage_name.argtypes = [i]
     L.mgs_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
-    if L.mgs_abi_version() != 101:
+    L.mgs_activate.restype = C.c_int
+    L.mgs_activate.argtypes = [i, i, vp, vp, vp, vp, vp, vp, vp, vp,   # P F means d_means rot d_rot scales d_scales opac feature
+                               i, f, i, i, i,                           # scale_mode scale_max opacity_mode rot_normalize feature_normalize
+                               vp, vp, vp, vp, vp, vp]                  # out_means out_rot out_scales out_opac out_feature stream
+    L.mgs_activate_backward.restype = C.c_int
+    L.mgs_activate_backward.argtypes = [i, i, vp, vp, vp, vp, vp, vp, vp, vp, i, f, i, i, i,
+                                        vp, vp, vp, vp, vp,             # g_means g_rot g_scales g_opac g_feature
+                                        vp, vp, vp, vp, vp, vp, vp, vp, # dL: means d_means rot d_rot scales d_scales opac feature
+                                        vp]
+    if L.mgs_abi_version() != 102:
         raise ImportError("manigaussian_b200: ABI version mismatch")
     _lib = L
     return L
@@ -75,6 +84,7 @@ EXPORTED_SYMBOLS = (
     "mgs_abi_version", "mgs_last_error", "mgs_geometry_state_bytes", "mgs_image_state_bytes",
     "mgs_binning_state_bytes", "mgs_backward_scratch_bytes", "mgs_forward", "mgs_forward_begin", "mgs_forward_finish",
     "mgs_backward",
+    "mgs_activate", "mgs_activate_backward",
     "mgs_mark_visible", "mgs_state_array", "mgs_profile_enable", "mgs_profile_num_stages",
     "mgs_profile_stage_name", "mgs_profile_read",
 )

@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libmgs_rasterizer.so")
-SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "api.cu"]
+SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "activate.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -42,7 +42,7 @@ static int fail(int code, const std::string& msg)
 	} while (0)
 
 // ---- optional per-stage CUDA-event timing (bench.py's roofline leg); off by default, zero cost when off ----
-enum Stage { ST_PROJECT_FWD = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_SORT, ST_RANGES_PACK, ST_BLEND_FWD, ST_BLEND_BWD, ST_PROJECT_BWD, ST_COUNT };
+enum Stage { ST_PROJECT_FWD = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_SORT, ST_RANGES_PACK, ST_BLEND_FWD, ST_BLEND_BWD, ST_PROJECT_BWD, ST_ACTIVATE_FWD, ST_ACTIVATE_BWD, ST_COUNT };
 struct StageEvt { int stage; cudaEvent_t a, b; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
@@ -166,7 +166,7 @@ using namespace mgs;
 
 extern "C" {
 
-int mgs_abi_version(void) { return 101; }
+int mgs_abi_version(void) { return 102; }
 const char* mgs_last_error(void) { return g_err.c_str(); }
 
 size_t mgs_geometry_state_bytes(int P) { return required([&](char*& p) { GeomState::carve(p, (size_t)P); }); }
@@ -441,6 +441,69 @@ int mgs_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 	return 0;
 }
 
+static int activate_common(ActivateArgs& a, int P, int F, const float* means, const float* d_means, const float* rot, const float* d_rot,
+	const float* scales, const float* d_scales, const float* opac, const float* feature,
+	int scale_mode, float scale_max, int opacity_mode, int rot_normalize, int feature_normalize)
+{
+	if (P < 0 || F < 0) return fail(MGS_ERR_INVALID_ARG, "bad P or F");
+	if (scale_mode < 0 || scale_mode > 1 || opacity_mode < 0 || opacity_mode > 1) return fail(MGS_ERR_INVALID_ARG, "unknown activation mode");
+	memset(&a, 0, sizeof(a));
+	a.P = P; a.F = F;
+	a.means = means; a.d_means = d_means; a.rot = rot; a.d_rot = d_rot; a.scales = scales; a.d_scales = d_scales;
+	a.opac = opac; a.feature = F > 0 ? feature : nullptr;
+	a.scale_mode = scale_mode; a.scale_max = scale_max; a.opacity_mode = opacity_mode;
+	a.rot_normalize = rot_normalize != 0; a.feature_normalize = feature_normalize != 0;
+	return 0;
+}
+
+int mgs_activate(int P, int F,
+	const float* means, const float* d_means, const float* rot, const float* d_rot,
+	const float* scales, const float* d_scales, const float* opac, const float* feature,
+	int scale_mode, float scale_max, int opacity_mode, int rot_normalize, int feature_normalize,
+	float* out_means, float* out_rot, float* out_scales, float* out_opac, float* out_feature,
+	void* stream)
+{
+	ActivateArgs a;
+	int rc = activate_common(a, P, F, means, d_means, rot, d_rot, scales, d_scales, opac, feature,
+		scale_mode, scale_max, opacity_mode, rot_normalize, feature_normalize);
+	if (rc) return rc;
+	if (P == 0) return 0;
+	if ((out_means && !means) || (out_rot && !rot) || (out_scales && !scales) || (out_opac && !opac) || (out_feature && F > 0 && !feature))
+		return fail(MGS_ERR_INVALID_ARG, "an output was requested for an input that is NULL");
+	a.o_means = out_means; a.o_rot = out_rot; a.o_scales = out_scales; a.o_opac = out_opac; a.o_feature = F > 0 ? out_feature : nullptr;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	{ StageTimer t_(ST_ACTIVATE_FWD, st); launch_activate_fwd(a, st); }
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(MGS_ERR_CUDA, std::string("activate: ") + cudaGetErrorString(e));
+	return 0;
+}
+
+int mgs_activate_backward(int P, int F,
+	const float* means, const float* d_means, const float* rot, const float* d_rot,
+	const float* scales, const float* d_scales, const float* opac, const float* feature,
+	int scale_mode, float scale_max, int opacity_mode, int rot_normalize, int feature_normalize,
+	const float* g_means, const float* g_rot, const float* g_scales, const float* g_opac, const float* g_feature,
+	float* dL_dmeans, float* dL_dd_means, float* dL_drot, float* dL_dd_rot,
+	float* dL_dscales, float* dL_dd_scales, float* dL_dopac, float* dL_dfeature,
+	void* stream)
+{
+	ActivateArgs a;
+	int rc = activate_common(a, P, F, means, d_means, rot, d_rot, scales, d_scales, opac, feature,
+		scale_mode, scale_max, opacity_mode, rot_normalize, feature_normalize);
+	if (rc) return rc;
+	if (P == 0) return 0;
+	if ((g_rot && !rot) || (g_scales && scale_mode == 1 && !scales) || (g_opac && opacity_mode == 1 && !opac) || (g_feature && F > 0 && !feature))
+		return fail(MGS_ERR_INVALID_ARG, "a gradient was given for an input that is NULL");
+	a.g_means = g_means; a.g_rot = g_rot; a.g_scales = g_scales; a.g_opac = g_opac; a.g_feature = F > 0 ? g_feature : nullptr;
+	a.dL_means = dL_dmeans; a.dL_dmeans = dL_dd_means; a.dL_rot = dL_drot; a.dL_drot = dL_dd_rot;
+	a.dL_scales = dL_dscales; a.dL_dscales = dL_dd_scales; a.dL_opac = dL_dopac; a.dL_feature = F > 0 ? dL_dfeature : nullptr;
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	{ StageTimer t_(ST_ACTIVATE_BWD, st); launch_activate_bwd(a, st); }
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(MGS_ERR_CUDA, std::string("activate_backward: ") + cudaGetErrorString(e));
+	return 0;
+}
+
 int mgs_profile_enable(int on)
 {
 	std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -453,7 +516,7 @@ int mgs_profile_enable(int on)
 int mgs_profile_num_stages(void) { return ST_COUNT; }
 const char* mgs_profile_stage_name(int i)
 {
-	static const char* names[ST_COUNT] = { "project_fwd", "depth_sort", "scan", "emit_tiles", "tile_sort", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd" };
+	static const char* names[ST_COUNT] = { "project_fwd", "depth_sort", "scan", "emit_tiles", "tile_sort", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd", "activate_fwd", "activate_bwd" };
 	return (i >= 0 && i < ST_COUNT) ? names[i] : "";
 }
 int mgs_profile_read(float* total_ms, int* counts)

@@ -93,6 +93,34 @@ struct BlendArgs {
 	float* dL_dfeat;             // [P,F] (zeroed by caller) nullable
 };
 
+// activate.cu: view-independent per-Gaussian pre-ops (activations, deformation offsets, feature normalisation)
+struct ActivateArgs {
+	int P, F;
+	const float* means;     // [P,3]
+	const float* d_means;   // [P,3] offset added before use, nullable
+	const float* rot;       // [P,4]
+	const float* d_rot;     // [P,4] nullable
+	const float* scales;    // [P,3]
+	const float* d_scales;  // [P,3] nullable
+	const float* opac;      // [P]
+	const float* feature;   // [P,F] nullable
+	int scale_mode;         // 0 identity, 1 min(exp(x), scale_max)
+	float scale_max;
+	int opacity_mode;       // 0 identity, 1 sigmoid
+	int rot_normalize;      // x / max(||x||, 1e-12)
+	int feature_normalize;  // x / (||x|| + 1e-12)
+	// forward outputs (a null output skips that field)
+	float *o_means, *o_rot, *o_scales, *o_opac, *o_feature;
+	// backward inputs: gradients w.r.t. the activated arrays (a null input skips that field)
+	const float *g_means, *g_rot, *g_scales, *g_opac, *g_feature;
+	// backward outputs: gradients w.r.t. the raw arrays and (same values) the offsets; each nullable
+	float *dL_means, *dL_dmeans, *dL_rot, *dL_drot, *dL_scales, *dL_dscales, *dL_opac, *dL_feature;
+	// filled by the launcher
+	int small_blocks, feature_group;
+};
+void launch_activate_fwd(ActivateArgs a, cudaStream_t s);
+void launch_activate_bwd(ActivateArgs a, cudaStream_t s);
+
 void launch_project_fwd(const ProjectFwdArgs& a, cudaStream_t s);
 void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);

@@ -9,7 +9,7 @@ The reference has no counterpart: it renders one view per call on one GPU and le
 """
 import torch
 
-FIELDS = ("dL_dmeans3D", "dL_dmeans2D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dsh", "dL_dfeature")
+FIELDS = ("dL_dmeans3D", "dL_dmeans2D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dsh", "dL_dfeature", "dL_dcolors")
 
 
 def shard_views(total_views, rank, world):
@@ -18,8 +18,10 @@ def shard_views(total_views, rank, world):
 
 
 class PackedGradients:
-    def __init__(self, P, F, M, device):
-        self.widths = dict(dL_dmeans3D=3, dL_dmeans2D=3, dL_dscales=3, dL_drotations=4, dL_dopacity=1, dL_dsh=3 * M, dL_dfeature=F)
+    def __init__(self, P, F, M, device, colors=False):
+        """colors=True adds a [P,3] field for precomputed-colour gradients (used instead of SH when M == 0)."""
+        self.widths = dict(dL_dmeans3D=3, dL_dmeans2D=3, dL_dscales=3, dL_drotations=4, dL_dopacity=1, dL_dsh=3 * M, dL_dfeature=F,
+                           dL_dcolors=3 if colors else 0)
         self.P = P
         # every field starts on a 16-byte boundary so that 128-bit reductions can target it directly
         offs, off = {}, 0

@@ -163,7 +163,7 @@ def rasterize_gaussians_backward_raw(bg, means3D, radii, colors, language_featur
         dL_dscales, dL_drotations = acc.get("dL_dscales"), acc.get("dL_drotations")
         dL_dsh = acc.get("dL_dsh") if M else torch.empty((P, 0, 3), **opts)
         dL_dfeature = acc.get("dL_dfeature") if F else torch.zeros((1,), **opts)
-        dL_dcolors, dL_dcov3D = None, None
+        dL_dcolors, dL_dcov3D = acc.get("dL_dcolors"), None
     else:
         dL_dmeans3D = torch.empty((P, 3), **opts)
         dL_dmeans2D = torch.empty((P, 3), **opts)
@@ -361,12 +361,14 @@ def _view_streams(device, n):
 
 
 def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scales, rotations, scale_modifier, cov3D_precomp,
-                        sh, degree, include_feature, return_depth=False, debug=False, after_view=None):
+                        sh, degree, include_feature, return_depth=False, debug=False, after_view=None, out_buffers=None):
     """Forward of V views of one Gaussian cloud.  `views` is a sequence of GaussianRasterizationSettings (bg, viewmatrix,
     projmatrix, tanfov*, image size, campos are read per view).  Returns (outs, streams): outs[v] has the layout of
     rasterize_gaussians_raw's result; work of view v is enqueued on streams[v] (callers that consume the outputs on
     another stream must wait on it; rasterize_views_backward_raw does).  `after_view(v, out)` is called inside view v's
-    stream context as soon as its forward is enqueued (e.g. to enqueue that view's backward before finishing the next view)."""
+    stream context as soon as its forward is enqueued (e.g. to enqueue that view's backward before finishing the next view).
+    `out_buffers` = (color [V,3,H,W], feature [V,F,H,W] or None, depth [V,H,W] or None): render straight into slices of
+    caller-owned batch tensors instead of per-view allocations."""
     L = _b.lib()
     dev = means3D.device
     if not means3D.is_cuda:
@@ -417,10 +419,15 @@ def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scale
         for v, (st, H, W, bg, vm, pm, cp, radii, ga, ia, ba) in enumerate(pend):
             R, geom, img, binb = mid[v]
             with torch.cuda.stream(st):
-                out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-                out_feature = torch.empty((F, H, W), dtype=torch.float32, device=dev) if include_feature else \
-                    torch.zeros((1,), dtype=torch.float32, device=dev)
-                out_depth = torch.empty((H, W), dtype=torch.float32, device=dev) if return_depth else None
+                if out_buffers is not None:
+                    out_color = out_buffers[0][v]
+                    out_feature = out_buffers[1][v] if (include_feature and F) else torch.zeros((1,), dtype=torch.float32, device=dev)
+                    out_depth = out_buffers[2][v] if return_depth else None
+                else:
+                    out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+                    out_feature = torch.empty((F, H, W), dtype=torch.float32, device=dev) if include_feature else \
+                        torch.zeros((1,), dtype=torch.float32, device=dev)
+                    out_depth = torch.empty((H, W), dtype=torch.float32, device=dev) if return_depth else None
                 _b.check(L.mgs_forward_finish(
                     _ALLOC_CB, None, _ptr(binb), _ptr(geom), _ptr(img), P, F, W, H, _ptr(bg), _ptr(language_feature) if F else None,
                     _ptr(radii), R, _ptr(out_color), _ptr(out_feature) if F else None, _ptr(out_depth), 2, int(bool(debug)),
@@ -434,9 +441,11 @@ def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scale
 
 def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_feature, means3D, colors, language_feature, scales,
                                  rotations, scale_modifier, cov3D_precomp, sh, degree, include_feature, grads_depth=None,
-                                 debug=False, accumulate_into=None):
+                                 debug=False, accumulate_into=None, means2D_per_view=None):
     """Backward of the V views rendered by rasterize_views_raw, each on its view's stream.  Returns a list of the
-    9-tuples of rasterize_gaussians_backward_raw.  The caller's current stream waits for all of them on return."""
+    9-tuples of rasterize_gaussians_backward_raw.  The caller's current stream waits for all of them on return.
+    With `accumulate_into`, `means2D_per_view` (zeroed [V,P,3]) keeps the screen-space gradients of each view apart
+    (the reference's per-render `viewspace_points.grad`) while everything else is summed over views."""
     dev = means3D.device
     main = torch.cuda.current_stream(dev)
     res = []
@@ -449,7 +458,9 @@ def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_featur
                 s.bg, means3D, o[3], colors, language_feature, scales, rotations, scale_modifier, cov3D_precomp, s.viewmatrix,
                 s.projmatrix, s.tanfovx, s.tanfovy, grads_color[v], grads_feature[v] if grads_feature is not None else None, sh,
                 degree, s.campos, o[4], o[0], o[5], o[6], debug, include_feature,
-                dL_dout_depth=grads_depth[v] if grads_depth is not None else None, accumulate_into=accumulate_into))
+                dL_dout_depth=grads_depth[v] if grads_depth is not None else None,
+                accumulate_into=(dict(accumulate_into, dL_dmeans2D=means2D_per_view[v])
+                                 if (accumulate_into is not None and means2D_per_view is not None) else accumulate_into)))
     for st in streams[:len(views)]:
         main.wait_stream(st)
     return res

@@ -97,7 +97,7 @@ def test_backward_matches_finite_differences(field, gname):
     assert np.linalg.norm(num - ana) <= tol * max(np.linalg.norm(ana), 1e-3), (field, num, ana)
 
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "g[0-9]*.npz")))
 
 
 @pytest.mark.skipif(not GOLDEN, reason="tests/golden/*.npz not generated yet (tests/golden/make_golden.py on a B200)")
