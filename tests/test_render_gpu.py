@@ -45,7 +45,7 @@ def test_fused_activations_match_torch_golden_and_oracle(name):
         assert torch.equal(n[2], scales.detach()) and torch.equal(n[3], opac.detach())
         if F:
             # the reference normalises the (already unit) features again on the next-frame render
-            assert util.rel_l2(n[4].cpu().numpy(), z["next_out_feature"]) < ACT_TOL
+            assert util.rel_l2(n[4].detach().cpu().numpy(), z["next_out_feature"]) < ACT_TOL
         loss = loss + (n[0] * _t(z["next_cot_means"])).sum() + (n[1] * _t(z["next_cot_rot"])).sum()
     loss.backward()
     pairs = [(xyz_maps, "grad_xyz_maps"), (rot_maps, "grad_rot_maps"), (scale_maps, "grad_scale_maps"), (opacity_maps, "grad_opacity_maps")]
