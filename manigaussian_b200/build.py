@@ -15,8 +15,12 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
-OBJDIR = os.path.join(LIBDIR, "obj")
-LIB = os.path.join(LIBDIR, "libmgs_rasterizer.so")
+OBJDIR = os.path.join(LIBDIR, "obj" + (("_" + os.environ["MGS_VARIANT"]) if os.environ.get("MGS_VARIANT") else ""))
+# experiment hooks: MGS_VARIANT names an alternative library built with MGS_NVCC_DEFINES (e.g. "-DMGS_FWD_NSUB=4"); the
+# default build ignores both
+VARIANT = os.environ.get("MGS_VARIANT", "")
+EXTRA = os.environ.get("MGS_NVCC_DEFINES", "").split() if VARIANT else []
+LIB = os.path.join(LIBDIR, "libmgs_rasterizer%s.so" % (("_" + VARIANT) if VARIANT else ""))
 SOURCES = ["project.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "activate.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -37,12 +41,13 @@ def _stamp():
         with open(f, "rb") as fh:
             h.update(f.encode())
             h.update(fh.read())
+    h.update(" ".join(EXTRA).encode())
     return h.hexdigest()
 
 
 def build(force=False, verbose=False):
     os.makedirs(OBJDIR, exist_ok=True)
-    stamp_file = os.path.join(LIBDIR, "build.stamp")
+    stamp_file = os.path.join(LIBDIR, "build%s.stamp" % (("_" + VARIANT) if VARIANT else ""))
     stamp = _stamp()
     if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
@@ -53,7 +58,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [NVCC] + ARCH + CFLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + ARCH + CFLAGS + EXTRA + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, r
 
@@ -65,7 +70,7 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
-    with open(os.path.join(LIBDIR, "ptxas.log"), "w") as fh:
+    with open(os.path.join(LIBDIR, "ptxas%s.log" % (("_" + VARIANT) if VARIANT else "")), "w") as fh:
         fh.write("\n".join(log))
     if verbose:
         print("\n".join(log))

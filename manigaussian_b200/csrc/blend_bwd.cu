@@ -10,10 +10,10 @@
 // A_k = S_k-vector / T_{k+1}.  Using the scalar keeps the per-pixel carried state to two floats.
 //
 // B200 design: GAUSSIAN-parallel inside a single-warp CTA (blend_common.cuh).  The reference has every
-// pixel-thread issue 9+F global float atomics per contributing pair (41 at F=32).  Here a warp owns an 8x4 pixel
-// block; it streams the first max(n_contrib) records of its tile back to front through its TMA ring, culls them
+// pixel-thread issue 9+F global float atomics per contributing pair (41 at F=32).  Here a warp owns a BWD_BW x BWD_BH
+// pixel block; it streams the first max(n_contrib) records of its tile back to front through its TMA ring, culls them
 // against the block and queues the survivors; whenever 32 are queued, lane l takes the l-th one and keeps its
-// channel row and ALL of its gradient accumulators in registers while the warp walks the 32 pixels.  The per-pixel
+// channel row and ALL of its gradient accumulators in registers while the warp walks the block's pixels.  The per-pixel
 // sequential dependences (transmittance, S) across the 32 Gaussians of a chunk are resolved with warp prefix
 // scans.  No cross-lane reduction of the 9+F gradients is needed, and each (block, Gaussian) pair costs
 // ceil((12+F)/4) 128-bit red.global.add.v4.f32 instead of 9+F scalar atomics per pixel.  Pixel cotangent rows are
@@ -22,6 +22,20 @@
 
 namespace mgs {
 
+#ifndef MGS_BWD_BW
+#define MGS_BWD_BW 4
+#endif
+#ifndef MGS_BWD_BH
+#define MGS_BWD_BH 4
+#endif
+// Pixel block of one backward CTA.  The pixel walk costs (survivors of the block) x (pixels of the block), so for splats
+// of a few pixels a smaller block wastes less work on (Gaussian, pixel) pairs that do not touch; the price is one more
+// cull of the tile's list and one more gradient flush per (Gaussian, block) pair.  Measured on B200 at c3 (ms per view):
+// 8x4 0.641, 4x4 0.533, 8x2 0.582, 4x2 0.572, 2x2 0.768.
+constexpr int BWD_BW = MGS_BWD_BW, BWD_BH = MGS_BWD_BH;
+constexpr int BWD_NPX = BWD_BW * BWD_BH;                            // pixels per CTA (<= 32)
+constexpr int BWD_SUBS_X = TILE_X / BWD_BW, BWD_SUBS = BWD_SUBS_X * (TILE_Y / BWD_BH);  // CTAs per 16x16 tile
+static_assert(BWD_NPX <= 32 && TILE_X % BWD_BW == 0 && TILE_Y % BWD_BH == 0, "backward pixel block");
 constexpr int QCAP = 64;  // survivor queue capacity (power of two, >= 63)
 constexpr int PIX = 2;    // pixels interleaved per iteration of the pixel walk (instruction-level parallelism)
 constexpr int BWD_MIN_CTAS = PIX == 4 ? 8 : (PIX == 2 ? 12 : 16);
@@ -31,18 +45,18 @@ __global__ void __launch_bounds__(32, BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a
 {
 	__shared__ __align__(128) InstRec s_rec[RING * REC_BATCH];
 	__shared__ __align__(16) float4 s_queue[QCAP * 2];   // survivors: {x,y,ca,cb}, {cc,op,pos,id}
-	__shared__ __align__(16) float4 s_g[32 * NQ];         // [pixel][q] cotangent rows
-	__shared__ __align__(16) float4 s_state[32];          // {T, S, n_contrib, Tfinal*bg.g}
+	__shared__ __align__(16) float4 s_g[BWD_NPX * NQ];    // [pixel][q] cotangent rows
+	__shared__ __align__(16) float4 s_state[BWD_NPX];     // {T, S, n_contrib, Tfinal*bg.g}
 	__shared__ __align__(8) uint64_t s_bar[RING];
 
 	const int lane = threadIdx.x;
-	const int tile = blockIdx.x >> 3, sub = blockIdx.x & 7;
+	const int tile = blockIdx.x / BWD_SUBS, sub = blockIdx.x % BWD_SUBS;
 	const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
-	const int bx0 = tile_x * TILE_X + (sub & 1) * WARP_BX;
-	const int by0 = tile_y * TILE_Y + (sub >> 1) * WARP_BY;
-	const int pxi = bx0 + (lane & 7), pyi = by0 + (lane >> 3);
-	const bool inside = pxi < a.W && pyi < a.H;
-	const float fbx0 = (float)bx0, fbx1 = (float)(bx0 + WARP_BX - 1), fby0 = (float)by0, fby1 = (float)(by0 + WARP_BY - 1);
+	const int bx0 = tile_x * TILE_X + (sub % BWD_SUBS_X) * BWD_BW;
+	const int by0 = tile_y * TILE_Y + (sub / BWD_SUBS_X) * BWD_BH;
+	const int pxi = bx0 + (lane % BWD_BW), pyi = by0 + (lane / BWD_BW);
+	const bool inside = lane < BWD_NPX && pxi < a.W && pyi < a.H;
+	const float fbx0 = (float)bx0, fbx1 = (float)(bx0 + BWD_BW - 1), fby0 = (float)by0, fby1 = (float)(by0 + BWD_BH - 1);
 	const size_t HW = (size_t)a.H * a.W;
 	const size_t pix = (size_t)a.W * pyi + pxi;
 	const int F = a.F;
@@ -66,10 +80,12 @@ __global__ void __launch_bounds__(32, BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a
 					if (i < F) g[4 + i] = a.dL_dfeature[(size_t)i * HW + pix];
 			}
 		}
+		if (lane < BWD_NPX) {
 #pragma unroll
-		for (int q = 0; q < NQ; q++) s_g[lane * NQ + q] = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
-		const float bgdot = a.bg[0] * g[0] + a.bg[1] * g[1] + a.bg[2] * g[2];
-		s_state[lane] = make_float4(Tf, 0.f, __uint_as_float(nc), Tf * bgdot);
+			for (int q = 0; q < NQ; q++) s_g[lane * NQ + q] = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+			const float bgdot = a.bg[0] * g[0] + a.bg[1] * g[1] + a.bg[2] * g[2];
+			s_state[lane] = make_float4(Tf, 0.f, __uint_as_float(nc), Tf * bgdot);
+		}
 	}
 	uint32_t maxc = nc;
 #pragma unroll
@@ -127,7 +143,7 @@ __global__ void __launch_bounds__(32, BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a
 
 		// Two horizontally adjacent pixels per iteration: their scan chains (5 dependent shuffles each, twice) are
 		// independent, so interleaving them doubles the instruction-level parallelism of the latency-bound part.
-		for (int p = 0; p < 32; p += PIX) {
+		for (int p = 0; p < BWD_NPX; p += PIX) {
 			float4 st[PIX];
 			uint32_t ncp[PIX];
 			bool live_px = false;
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(32, BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a
 			bool any_valid = false;
 #pragma unroll
 			for (int u = 0; u < PIX; u++) {
-				const float pfx = (float)(bx0 + ((p + u) & 7)), pfy = (float)(by0 + ((p + u) >> 3));
+				const float pfx = (float)(bx0 + ((p + u) % BWD_BW)), pfy = (float)(by0 + ((p + u) / BWD_BW));
 				dx[u] = gx_ - pfx; dy[u] = gy_ - pfy;
 				const float power = -0.5f * (ca * dx[u] * dx[u] + cc * dy[u] * dy[u]) - cb * dx[u] * dy[u];
 				// ex2.approx-based exp (rel. error ~1e-6); the alpha >= 1/255 decision must agree with the forward's
@@ -280,7 +296,7 @@ bool feature_rows_vectorizable(const float* feature, int F);
 template <int NQ>
 static void launch_bwd_t(const BlendArgs& a, cudaStream_t s)
 {
-	const int grid = a.grid_x * a.grid_y * 8;
+	const int grid = a.grid_x * a.grid_y * BWD_SUBS;
 	const bool vec = NQ == 1 || (feature_rows_vectorizable(a.feature, a.F) && (reinterpret_cast<uintptr_t>(a.dL_dfeat) & 15) == 0);
 	if (vec) blend_bwd_kernel<NQ, true><<<grid, 32, 0, s>>>(a);
 	else blend_bwd_kernel<NQ, false><<<grid, 32, 0, s>>>(a);
