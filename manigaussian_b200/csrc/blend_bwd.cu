@@ -37,8 +37,15 @@ constexpr int BWD_NPX = BWD_BW * BWD_BH;                            // pixels pe
 constexpr int BWD_SUBS_X = TILE_X / BWD_BW, BWD_SUBS = BWD_SUBS_X * (TILE_Y / BWD_BH);  // CTAs per 16x16 tile
 static_assert(BWD_NPX <= 32 && TILE_X % BWD_BW == 0 && TILE_Y % BWD_BH == 0, "backward pixel block");
 constexpr int QCAP = 64;  // survivor queue capacity (power of two, >= 63)
-constexpr int PIX = 2;    // pixels interleaved per iteration of the pixel walk (instruction-level parallelism)
+#ifndef MGS_BWD_PIX
+#define MGS_BWD_PIX 2
+#endif
+constexpr int PIX = MGS_BWD_PIX;  // pixels interleaved per iteration of the pixel walk (instruction-level parallelism)
+#ifdef MGS_BWD_MIN_CTAS
+constexpr int BWD_MIN_CTAS = MGS_BWD_MIN_CTAS;
+#else
 constexpr int BWD_MIN_CTAS = PIX == 4 ? 8 : (PIX == 2 ? 12 : 16);
+#endif
 
 template <int NQ, bool VEC>
 __global__ void __launch_bounds__(32, BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a)

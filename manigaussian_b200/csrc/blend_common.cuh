@@ -14,7 +14,10 @@
 namespace mgs {
 
 constexpr int REC_BATCH = 64;  // records per bulk copy (2 KB) = two 32-record chunks
-constexpr int RING = 3;
+#ifndef MGS_RING
+#define MGS_RING 2
+#endif
+constexpr int RING = MGS_RING;  // record batches in flight / resident per warp
 
 // {x, y, ca, cb} and {cc, op, ext(half2 hx,hy), id} views of a record
 __device__ __forceinline__ float2 rec_extent(const float4& r1)
