@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(32, BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a
 			__syncwarp();
 			if (qcount >= 32) process_chunk(32);
 		}
-		// this batch's buffer is dead: refill it with the batch three ahead
+		// this batch's buffer is dead: refill it with the batch RING ahead
 		if (issued < nb) { ring.issue(issued); issued++; }
 	}
 	if (qcount > 0) process_chunk(qcount);

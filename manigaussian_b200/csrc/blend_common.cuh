@@ -2,7 +2,7 @@
 //
 // Work decomposition: ONE WARP = ONE CTA = one 8x4 pixel block of a 16x16 tile (tile ids / work lists stay the
 // reference's 16x16 tiles; eight single-warp CTAs share a tile's list).  A warp streams the tile's sorted 32-byte
-// instance records through its own 3-deep shared-memory ring with 1-D TMA bulk copies (SASS UBLKCP), one copy per
+// instance records through its own RING-deep shared-memory ring with 1-D TMA bulk copies (SASS UBLKCP), one copy per
 // batch of REC_BATCH records tracked by an mbarrier, culls each 32-record chunk against its pixel block, and works
 // on the survivors.  No CTA-wide barrier exists anywhere: warps of a heavy tile never wait for each other, finished
 // warps free their SM slot immediately, and the hardware scheduler balances the 8*T*V small CTAs across the 148 SMs.
@@ -17,7 +17,9 @@ constexpr int REC_BATCH = 64;  // records per bulk copy (2 KB) = two 32-record c
 #ifndef MGS_RING
 #define MGS_RING 2
 #endif
-constexpr int RING = MGS_RING;  // record batches in flight / resident per warp
+// record batches in flight / resident per warp.  2 beats 3 and 4 at c3 (3.74 vs 3.88 vs 3.93 ms per 4-view step): the kernels'
+// own times do not change, but the smaller footprint lets more CTAs of concurrently running views share an SM.
+constexpr int RING = MGS_RING;
 
 // {x, y, ca, cb} and {cc, op, ext(half2 hx,hy), id} views of a record
 __device__ __forceinline__ float2 rec_extent(const float4& r1)

@@ -9,7 +9,7 @@
 //    per-Gaussian alpha >= 1/255 footprint (exact-conservative; decided by ballot), so a pixel only evaluates
 //    Gaussians that can reach its block (about a third of the tile's list on the benchmark workload);
 //  * two-level software pipeline, all data movement asynchronous TMA (UBLKCP) tracked by mbarriers:
-//      records     : up to three 64-record batches in flight/resident (one contiguous bulk copy each),
+//      records     : RING 64-record batches in flight/resident (one contiguous bulk copy each),
 //      channel rows: for the SURVIVORS of chunk g+1, per survivor a 16-byte {r,g,b,depth} copy and an F*4-byte
 //                    feature-row copy, gathered by Gaussian id into a double-buffered row array while chunk g is blended;
 //  * channel rows are consumed from shared memory as 128-bit broadcasts instead of per-pair scalar global
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 			for (int k = waited; k < issued; k++) ring.wait(k);
 			break;
 		}
-		// the batch whose last chunk was just blended frees its buffer for the batch three ahead
+		// the batch whose last chunk was just blended frees its buffer for the batch RING ahead
 		if ((g & 1) && issued < nb) { ring.issue(issued); issued++; }
 		mask_cur = mask_next; my_cur = my_next; steps_cur = steps_next;
 	}
