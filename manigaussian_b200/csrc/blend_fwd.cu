@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 				last_contributor = pos0 + (uint32_t)b;
 			};
 			uint32_t mm = my_cur;  // per lane: the survivors of this lane's sub-block, nearest first
+			int i = 0;             // FWD_NSUB == 1: rank of the next survivor among the chunk's survivors (warp-uniform)
 			for (int it = 0; it < steps_cur; it += 2) {
 				const bool act0 = mm != 0;
 				const int b0 = act0 ? __ffs(mm) - 1 : 0;
@@ -179,8 +180,11 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 				const float a0 = q0.y * expf(power0);
 				const float a1 = q1.y * expf(power1);
 				// a survivor's channel row sits at its rank among the chunk's (union) survivors
-				blend_one(act0, b0, power0, a0, rows + __popc(mask_cur & ((1u << b0) - 1u)) * NQ);
-				blend_one(act1, b1, power1, a1, rows + __popc(mask_cur & ((1u << b1) - 1u)) * NQ);
+				const int r0i = FWD_NSUB == 1 ? i : __popc(mask_cur & ((1u << b0) - 1u));
+				const int r1i = FWD_NSUB == 1 ? i + 1 : __popc(mask_cur & ((1u << b1) - 1u));
+				blend_one(act0, b0, power0, a0, rows + r0i * NQ);
+				blend_one(act1, b1, power1, a1, rows + r1i * NQ);
+				i += 2;
 			}
 		}
 		if (__all_sync(0xffffffffu, done)) {
