@@ -588,6 +588,30 @@ def main_dyna(a, wl, base, cfg, torch, rank, world):
     out["gpu_launches"] = (6 * 2 * V + 4) * a.steps if a.impl == "ours" else 0
     out["roofline"] = {"bound": "hbm", "kernel": "whole pipeline", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                        "traffic": None, "note": "per-kernel roofline is reported by the c3 line (same rasterizer kernels)"}
+    if a.impl == "ours" and not a.no_stage_timing:
+        # the pre-op kernels are the HBM-bound part of this workload: time them alone (CUDA events inside the library)
+        from manigaussian_b200 import _binding
+        _binding.profile_read()
+        _binding.profile_enable(True)
+        for _ in range(3):
+            step(raw, C, T2)
+        torch.cuda.synchronize()
+        st = _binding.profile_read()
+        _binding.profile_enable(False)
+        per = {k: v[0] / max(v[1], 1) for k, v in st.items()}
+        cfg["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
+        # algorithmic bytes of the two launches per direction (current frame: all fields + F features; next frame: no features)
+        small = 4 * (3 + 4 + 3 + 1)
+        fwd_b = P * ((small + 12 + 4 * F) + (small + 4 * F)) + P * ((small + 12 + 16 + 12) + small)
+        bwd_b = P * ((small + 12 + 4 * F) + (small + 4 * F) + (small + 12 + 4 * F)) + P * ((small + 40) + small + (small + 40))
+        if per.get("activate_fwd", 0) > 0 and per.get("activate_bwd", 0) > 0:
+            ach_f = fwd_b / 2 / (per["activate_fwd"] * 1e-3) / 1e9
+            ach_b = bwd_b / 2 / (per["activate_bwd"] * 1e-3) / 1e9
+            out["roofline"] = {"bound": "hbm", "kernel": "activate_bwd", "achieved": ach_b, "peak": peak, "unit": "GB/s",
+                               "frac": ach_b / peak, "traffic": None, "ms_per_launch": per["activate_bwd"],
+                               "alg_bytes_per_launch": bwd_b / 2,
+                               "also": {"activate_fwd": {"achieved": ach_f, "frac": ach_f / peak, "ms_per_launch": per["activate_fwd"]}},
+                               "note": "mean of the current-frame and next-frame launches; the blend kernels' roofline is on the c3 line"}
     if a.gpus == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_baseline(wl)
         cb["sample"] += " [rasterizer of one frame; activations not included]"

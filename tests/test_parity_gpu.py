@@ -343,3 +343,32 @@ def test_dynamic_path_gradients_reach_deformation_offsets():
     assert util.rel_l2(tmu.grad.cpu().numpy(), bw["dL_dmeans3D"]) < tol_cov
     assert util.rel_l2(ts.grad.cpu().numpy(), bw["dL_dscales"]) < tol_cov
     assert util.rel_l2(tr.grad.cpu().numpy(), qt.grad.numpy()) < tol_cov
+
+
+@pytest.mark.parametrize("F", [1, 2, 4, 7, 9, 12, 20, 24, 31])
+def test_feature_width_sweep(F):
+    """Every run-time feature width dispatches to a padded channel-row layout (NQ in {2,3,5,9}); widths that are not a
+    multiple of four take the non-bulk-copy row path.  Ragged image so that partial tiles and partial blocks are hit."""
+    inp = util.make_inputs(P=700, W=41, H=27, F=F, seed=100 + F, bg=(0.2, 0.1, 0.7))
+    check_stagewise_vs_oracle(inp, 1e-3)
+
+
+@pytest.mark.parametrize("P,W,H", [(1, 16, 16), (3, 1, 1), (50, 17, 9), (200, 15, 33), (64, 300, 8)])
+def test_degenerate_sizes(P, W, H):
+    inp = util.make_inputs(P=P, W=W, H=H, F=32, seed=P + W)
+    check_stagewise_vs_oracle(inp, 1e-3)
+
+
+def test_opaque_scene_early_termination():
+    """Large, nearly opaque splats: most pixels stop at T < 1e-4 long before their tile's list ends (forward `done` path,
+    backward walks only the first n_contrib records); n_contrib is compared with the oracle inside the stage-wise check."""
+    inp = util.make_inputs(P=3000, W=96, H=96, F=32, seed=31, scale0=0.05)
+    inp["g"]["opacities"] = np.full_like(inp["g"]["opacities"], 0.95)
+    ours, _ = util.run_ours(inp)
+    lens = (ours["ranges"][:, 1] - ours["ranges"][:, 0]).astype(np.int64)
+    gx = (inp["W"] + 15) // 16
+    ys, xs = np.mgrid[0:inp["H"], 0:inp["W"]]
+    per_px_len = lens[(ys // 16) * gx + xs // 16].ravel()
+    stopped = (ours["final_T"].ravel() < 1e-3) & (ours["n_contrib"].ravel() < per_px_len)
+    assert stopped.mean() > 0.3, "the scene was meant to terminate early on a large share of the pixels"
+    check_stagewise_vs_oracle(inp, 1e-3)
