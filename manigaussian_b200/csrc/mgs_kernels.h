@@ -116,7 +116,7 @@ struct ActivateArgs {
 	// backward outputs: gradients w.r.t. the raw arrays and (same values) the offsets; each nullable
 	float *dL_means, *dL_dmeans, *dL_rot, *dL_drot, *dL_scales, *dL_dscales, *dL_opac, *dL_feature;
 	// filled by the launcher
-	int small_blocks, feature_group;
+	int small_blocks, feature_group, feature_group4, feature_vec4;
 };
 void launch_activate_fwd(ActivateArgs a, cudaStream_t s);
 void launch_activate_bwd(ActivateArgs a, cudaStream_t s);
