@@ -15,22 +15,17 @@
 //  * channel rows are consumed from shared memory as 128-bit broadcasts instead of per-pair scalar global
 //    gathers (forward.cu:364-371);
 //  * feature width is a run-time value dispatched to NQ = ceil((4+F)/4) in {1,2,3,5,9};
-//  * optional SUB-BLOCK LOCKSTEP (MGS_FWD_NSUB = 2 or 4; default 1 = off): the 8x4 block is split into two 4x4 or four
-//    4x2 sub-blocks, each chunk is also culled against every sub-block (one ballot each) and a lane walks only the
-//    survivors of ITS sub-block, all sub-blocks in lockstep -- Gaussians whose footprints lie in different sub-blocks
-//    commute.  Bit-identical results and ~25 % fewer walk steps on the benchmark cloud, but the per-lane list
-//    bookkeeping (ffs/popc/address math that is warp-uniform otherwise) costs as much as the steps save: measured on
-//    B200 at c3, 0.427 ms (off) vs 0.443 ms (2) vs 0.481 ms (4) per view.  Kept as a compile-time experiment.
+//  * two survivors are evaluated per step of the walk: their footprint evaluations are independent of the transmittance
+//    recurrence, so the second one's expf latency overlaps with the first one's channel FMAs.
+// Tried and rejected on B200 (all bit-identical; numbers per c3 view, this kernel 0.427 ms): "sub-block lockstep" (lanes of
+// the two 4x4 halves walk their own survivor lists in lockstep: 25 % fewer steps, 0.443 ms -- the per-lane bookkeeping
+// costs what the steps save) and a two-phase walk (phase A evaluates alpha for all survivors into shared memory, phase B
+// lets every lane blend only its own contributors: ncu shows 7 of 32 threads active in the channel FMAs here, yet
+// 0.429 ms -- the walk is bound by per-warp dependent-issue latency with 2-3 warps per scheduler, not by instruction
+// count; a pathological slowdown on dense scenes besides).
 #include "blend_common.cuh"
 
-#ifndef MGS_FWD_NSUB
-#define MGS_FWD_NSUB 1
-#endif
-
 namespace mgs {
-
-constexpr int FWD_NSUB = MGS_FWD_NSUB;
-static_assert(FWD_NSUB == 1 || FWD_NSUB == 2 || FWD_NSUB == 4, "sub-block split of the 8x4 block");
 
 template <int NQ, bool VEC>
 __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
@@ -50,8 +45,6 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 	if (__all_sync(0xffffffffu, !inside)) return;  // block entirely outside the image (ragged right/bottom tiles)
 	const float pfx = (float)pxi, pfy = (float)pyi;
 	const float fbx0 = (float)bx0, fbx1 = (float)(bx0 + WARP_BX - 1), fby0 = (float)by0, fby1 = (float)(by0 + WARP_BY - 1);
-	// this lane's sub-block: 4 columns wide when split in two, 4x2 when split in four
-	const int mysub = FWD_NSUB == 1 ? 0 : (((lane & 7) >> 2) + (FWD_NSUB == 4 ? 2 * (lane >> 4) : 0));
 	const int F = a.F;
 	const uint32_t row_bytes = 16u + (NQ > 1 ? (uint32_t)F * 4u : 0u);
 
@@ -76,8 +69,6 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 #pragma unroll
 	for (int i = 0; i < 4 * NQ; i++) acc[i] = 0.f;
 
-	uint32_t my_next = 0;  // survivors of this lane's sub-block in the chunk being prefetched
-	int steps_next = 0;    // max over the sub-blocks of their survivor counts
 	// cull chunk g and start gathering the survivors' channel rows into s_rows[g & 1]
 	auto prefetch_chunk = [&](int g) -> uint32_t {
 		const int k = g >> 1;
@@ -87,19 +78,6 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 		const int j = ((g & 1) << 5) + lane;
 		const bool hit = (g * 32 + lane < ring.total) && rec_hits_block(rec4[2 * j], rec4[2 * j + 1], fbx0, fbx1, fby0, fby1);
 		const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-		my_next = mask; steps_next = __popc(mask);
-		if (FWD_NSUB > 1 && mask) {
-			steps_next = 0;
-#pragma unroll
-			for (int sb = 0; sb < FWD_NSUB; sb++) {
-				const float sx0 = fbx0 + 4.f * (sb & 1), sy0 = FWD_NSUB == 4 ? fby0 + 2.f * (sb >> 1) : fby0;
-				const float sy1 = FWD_NSUB == 4 ? sy0 + 1.f : fby1;
-				const bool hs = hit && rec_hits_block(rec4[2 * j], rec4[2 * j + 1], sx0, sx0 + 3.f, sy0, sy1);
-				const uint32_t ms = __ballot_sync(0xffffffffu, hs);
-				if (mysub == sb) my_next = ms;
-				steps_next = max(steps_next, __popc(ms));
-			}
-		}
 		if (mask) {
 			float4* rows = s_rows[g & 1];
 			const int rank = __popc(mask & ((1u << lane) - 1u));
@@ -128,12 +106,10 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 		return mask;
 	};
 
-	uint32_t mask_cur = 0, mask_next = 0, my_cur = 0;
-	int steps_cur = 0;
+	uint32_t mask_cur = 0, mask_next = 0;
 	if (nchunks > 0) {
 		for (; issued < min(nb, RING); issued++) ring.issue(issued);
 		mask_cur = prefetch_chunk(0);
-		my_cur = my_next; steps_cur = steps_next;
 	}
 	for (int g = 0; g < nchunks; g++) {
 		mask_next = 0;
@@ -145,10 +121,9 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 			const float4* rec4 = ring.buffer(g >> 1) + (rb << 6);
 			const float4* rows = s_rows[rb];
 			const uint32_t pos0 = (uint32_t)(g * 32) + 1u;  // 1-based position of the chunk's first record in the tile list
-			// Two survivors per step: their footprint evaluations (power, expf) are independent of the transmittance
-			// recurrence, so issuing both up front overlaps the second one's latency with the first one's channel FMAs.
-			auto blend_one = [&](bool act, int b, float power, float alpha_raw, const float4* row) {
-				if (!act || done || power > 0.0f) return;
+			// two survivors per step (see the header)
+			auto blend_one = [&](int b, float power, float alpha_raw, const float4* row) {
+				if (done || power > 0.0f) return;
 				const float alpha = min(ALPHA_MAX, alpha_raw);
 				if (alpha < ALPHA_MIN) return;
 				const float test_T = T * (1 - alpha);
@@ -163,15 +138,14 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 				T = test_T;
 				last_contributor = pos0 + (uint32_t)b;
 			};
-			uint32_t mm = my_cur;  // per lane: the survivors of this lane's sub-block, nearest first
-			int i = 0;             // FWD_NSUB == 1: rank of the next survivor among the chunk's survivors (warp-uniform)
-			for (int it = 0; it < steps_cur; it += 2) {
-				const bool act0 = mm != 0;
-				const int b0 = act0 ? __ffs(mm) - 1 : 0;
-				mm &= mm - 1;
-				const bool act1 = mm != 0;
-				const int b1 = act1 ? __ffs(mm) - 1 : b0;
-				mm &= mm - 1;
+			int i = 0;
+			uint32_t mask = mask_cur;
+			while (mask) {
+				const int b0 = __ffs(mask) - 1;
+				mask &= mask - 1;
+				const bool two = mask != 0;
+				const int b1 = two ? __ffs(mask) - 1 : b0;
+				if (two) mask &= mask - 1;
 				const float4 p0 = rec4[2 * b0], q0 = rec4[2 * b0 + 1];  // {x, y, ca, cb}, {cc, op, ext, id}
 				const float4 p1 = rec4[2 * b1], q1 = rec4[2 * b1 + 1];
 				const float dx0 = p0.x - pfx, dy0 = p0.y - pfy, dx1 = p1.x - pfx, dy1 = p1.y - pfy;
@@ -179,12 +153,9 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 				const float power1 = -0.5f * (p1.z * dx1 * dx1 + q1.x * dy1 * dy1) - p1.w * dx1 * dy1;
 				const float a0 = q0.y * expf(power0);
 				const float a1 = q1.y * expf(power1);
-				// a survivor's channel row sits at its rank among the chunk's (union) survivors
-				const int r0i = FWD_NSUB == 1 ? i : __popc(mask_cur & ((1u << b0) - 1u));
-				const int r1i = FWD_NSUB == 1 ? i + 1 : __popc(mask_cur & ((1u << b1) - 1u));
-				blend_one(act0, b0, power0, a0, rows + r0i * NQ);
-				blend_one(act1, b1, power1, a1, rows + r1i * NQ);
-				i += 2;
+				blend_one(b0, power0, a0, rows + i * NQ);
+				if (two) blend_one(b1, power1, a1, rows + (i + 1) * NQ);
+				i += two ? 2 : 1;
 			}
 		}
 		if (__all_sync(0xffffffffu, done)) {
@@ -195,7 +166,7 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 		}
 		// the batch whose last chunk was just blended frees its buffer for the batch RING ahead
 		if ((g & 1) && issued < nb) { ring.issue(issued); issued++; }
-		mask_cur = mask_next; my_cur = my_next; steps_cur = steps_next;
+		mask_cur = mask_next;
 	}
 
 	if (inside) {
