@@ -2,7 +2,7 @@
 # multi-GPU contract path: torchrun launch exactly as the driver does (short timeouts: a hang costs N x GPU-minutes)
 N=${1:-2}
 mkdir -p gpurun_out
-echo "== view-parallel check N=$N"; timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29510 tools/check_view_parallel.py 2>&1 | grep -v Warning | tail -3 | cut -c1-300
+echo "== view-parallel check N=$N"; timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29510 tools/check_view_parallel.py > gpurun_out/view_parallel_$N.log 2>&1; grep -v Warning gpurun_out/view_parallel_$N.log | tail -2 | cut -c1-300
 echo "== ours N=$N"; timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/scale_ours_$N.json 2> gpurun_out/scale_ours_$N.err; echo rc=$?; grep -v Warning gpurun_out/scale_ours_$N.err | tail -3 | cut -c1-300
 echo "== ref N=$N"; timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $N --steps 10 --warmup 3 > gpurun_out/scale_ref_$N.json 2> gpurun_out/scale_ref_$N.err; echo rc=$?; grep -v Warning gpurun_out/scale_ref_$N.err | tail -3 | cut -c1-300
 python - <<PY
