@@ -21,7 +21,6 @@ CPU leg of both arms is the oracle port.  Under torchrun (N > 1) views are shard
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

@@ -8,10 +8,13 @@
 //  * one single-warp CTA per 8x4 pixel block; the warp culls its tile's work list against the block with the
 //    per-Gaussian alpha >= 1/255 footprint (exact-conservative; decided by ballot), so a pixel only evaluates
 //    Gaussians that can reach its block (about a third of the tile's list on the benchmark workload);
-//  * two-level software pipeline, all data movement asynchronous TMA (UBLKCP) tracked by mbarriers:
-//      records     : RING 64-record batches in flight/resident (one contiguous bulk copy each),
-//      channel rows: for the SURVIVORS of chunk g+1, per survivor a 16-byte {r,g,b,depth} copy and an F*4-byte
-//                    feature-row copy, gathered by Gaussian id into a double-buffered row array while chunk g is blended;
+//  * two-level software pipeline, all data movement asynchronous:
+//      records     : RING 64-record batches in flight/resident, one contiguous 1-D TMA bulk copy each (UBLKCP + mbarrier);
+//      channel rows: while chunk g is blended, the {r,g,b,depth} quad and the F-float feature row of every SURVIVOR of
+//                    chunk g+1 are gathered by Gaussian id into a double-buffered row array with 16-byte cp.async
+//                    (LDGSTS) pieces spread over the lanes, one commit group per chunk.  (A bulk copy per survivor was
+//                    the first design; UBLKCP takes uniform operands, so the compiler serialised it into a loop trip per
+//                    survivor and copy -- 15 % of the kernel's stall samples.  LDGSTS: 0.426 -> 0.374 ms per c3 view.)
 //  * channel rows are consumed from shared memory as 128-bit broadcasts instead of per-pair scalar global
 //    gathers (forward.cu:364-371);
 //  * feature width is a run-time value dispatched to NQ = ceil((4+F)/4) in {1,2,3,5,9};
@@ -33,7 +36,7 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 	__shared__ __align__(128) InstRec s_rec[RING * REC_BATCH];
 	__shared__ __align__(16) float4 s_rows[2][32 * NQ];
 	__shared__ __align__(8) uint64_t s_bar_rec[RING];
-	__shared__ __align__(8) uint64_t s_bar_row[2];
+	__shared__ uint32_t s_ids[32];  // Gaussian ids of the chunk's survivors by rank (row gather addressing)
 
 	const int lane = threadIdx.x;
 	const int tile = blockIdx.x >> 3, sub = blockIdx.x & 7;
@@ -46,21 +49,13 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 	const float pfx = (float)pxi, pfy = (float)pyi;
 	const float fbx0 = (float)bx0, fbx1 = (float)(bx0 + WARP_BX - 1), fby0 = (float)by0, fby1 = (float)(by0 + WARP_BY - 1);
 	const int F = a.F;
-	const uint32_t row_bytes = 16u + (NQ > 1 ? (uint32_t)F * 4u : 0u);
 
 	const uint2 range = a.ranges[tile];
 	WarpRecRing ring;
 	ring.init(s_rec, s_bar_rec, a.recs + range.x, (int)(range.y - range.x), false);
-	if (lane == 0) {
-		mbar_init(&s_bar_row[0], 1);
-		mbar_init(&s_bar_row[1], 1);
-		mbar_fence_init();
-	}
-	__syncwarp();
 	const int nb = ring.num_batches();
 	const int nchunks = (ring.total + 31) >> 5;
 	int issued = 0, waited = 0;      // record batches
-	uint32_t row_parity = 0;          // bit b = parity of the next phase to wait for on s_bar_row[b]
 
 	float T = 1.0f;
 	uint32_t last_contributor = 0;
@@ -82,15 +77,17 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 			float4* rows = s_rows[g & 1];
 			const int rank = __popc(mask & ((1u << lane) - 1u));
 			if (VEC) {
-				if (lane == 0) {
-					fence_proxy_async();
-					mbar_arrive_expect_tx(&s_bar_row[g & 1], (uint32_t)__popc(mask) * row_bytes);
-				}
+				// cooperative gather: the rows of all survivors are cut into 16-byte pieces and every lane copies pieces
+				// lane, lane+32, ... with per-lane addresses (LDGSTS).  A per-survivor bulk copy (UBLKCP) takes uniform
+				// operands, so the compiler serialises it into one loop trip per survivor and copy.
+				if (hit) s_ids[rank] = rec_id(rec4[2 * j + 1]);
 				__syncwarp();
-				if (hit) {
-					const uint32_t id = rec_id(rec4[2 * j + 1]);
-					bulk_g2s(rows + rank * NQ, a.rgbd + id, 16u, &s_bar_row[g & 1]);
-					if (NQ > 1) bulk_g2s(rows + rank * NQ + 1, a.feature + (size_t)id * F, (uint32_t)F * 4u, &s_bar_row[g & 1]);
+				const int npieces = __popc(mask) * NQ;
+				for (int idx = lane; idx < npieces; idx += 32) {
+					const int r = idx / NQ, q = idx - r * NQ;
+					const uint32_t id = s_ids[r];
+					const float4* src = (q == 0) ? (a.rgbd + id) : (reinterpret_cast<const float4*>(a.feature + (size_t)id * F) + (q - 1));
+					cp_async16(rows + idx, src);
 				}
 			} else if (hit) {  // rows that are not 16-byte multiples (e.g. F = 3): plain loads
 				const uint32_t id = rec_id(rec4[2 * j + 1]);
@@ -103,6 +100,7 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 				}
 			}
 		}
+		if (VEC) cp_async_commit();  // one group per prefetched chunk, empty or not: wait_group counts stay uniform
 		return mask;
 	};
 
@@ -116,8 +114,11 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 		if (g + 1 < nchunks) mask_next = prefetch_chunk(g + 1);
 		if (mask_cur) {
 			const int rb = g & 1;
-			if (VEC) { mbar_wait(&s_bar_row[rb], (row_parity >> rb) & 1u); row_parity ^= 1u << rb; }
-			else __syncwarp();
+			if (VEC) {
+				// groups complete in order: all but the newest one (chunk g+1, if it was prefetched) must have landed
+				if (g + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
+			}
+			__syncwarp();
 			const float4* rec4 = ring.buffer(g >> 1) + (rb << 6);
 			const float4* rows = s_rows[rb];
 			const uint32_t pos0 = (uint32_t)(g * 32) + 1u;  // 1-based position of the chunk's first record in the tile list
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 		}
 		if (__all_sync(0xffffffffu, done)) {
 			// drain whatever is still in flight before the CTA exits
-			if (VEC && mask_next) mbar_wait(&s_bar_row[(g + 1) & 1], (row_parity >> ((g + 1) & 1)) & 1u);
+			if (VEC) cp_async_wait<0>();
 			for (int k = waited; k < issued; k++) ring.wait(k);
 			break;
 		}

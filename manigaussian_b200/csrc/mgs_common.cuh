@@ -133,6 +133,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 		::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 // 128-bit vector reduction to global memory (sm_90+): one L2 atomic transaction for 4 floats.
+// 16-byte asynchronous copy global -> shared with a PER-LANE address (SASS LDGSTS), tracked by per-thread commit groups
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
 {
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

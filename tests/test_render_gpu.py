@@ -107,7 +107,7 @@ def test_render_is_the_reference_pipeline():
     (gaussian_renderer/__init__.py:17-94) -- bit for bit on the images (the fused normalisation differs by an ulp, so the
     comparison feeds our normalised features to the module path) and within 1e-5 on gradients; and against the CPU oracle."""
     import torch
-    from manigaussian_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    from manigaussian_b200 import GaussianRasterizer
     from manigaussian_b200.gaussian_renderer import render, normalize_features
     P, F, W, H = 5000, 32, 96, 80
     g = _cloud(P, F, 21)
