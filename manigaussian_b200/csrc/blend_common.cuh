@@ -28,7 +28,11 @@ __device__ __forceinline__ float2 rec_extent(const float4& r1)
 }
 __device__ __forceinline__ uint32_t rec_id(const float4& r1) { return __float_as_uint(r1.w); }
 
-// does the alpha >= 1/255 footprint of the record overlap the pixel block [x0,x1] x [y0,y1]?
+// does the alpha >= 1/255 footprint of the record overlap the pixel block [x0,x1] x [y0,y1]?  Axis-aligned extent of the
+// footprint ellipse against the block; conservative.  (The exact ellipse-vs-rectangle test -- minimum of the conic's
+// quadratic form over the block against the level 2 ln(255 o) -- removes another 8-12 % of the survivors, but its ~25
+// instructions on the per-chunk critical path cost what the survivors save: forward 0.372 -> 0.388 ms, backward 0.528
+// -> 0.522 ms per c3 view.  Not kept.)
 __device__ __forceinline__ bool rec_hits_block(const float4& r0, const float4& r1, float x0, float x1, float y0, float y1)
 {
 	const float2 e = rec_extent(r1);
