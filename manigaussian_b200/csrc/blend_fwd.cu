@@ -25,7 +25,7 @@
 // costs what the steps save) and a two-phase walk (phase A evaluates alpha for all survivors into shared memory, phase B
 // lets every lane blend only its own contributors: ncu shows 7 of 32 threads active in the channel FMAs here, yet
 // 0.429 ms -- the walk is bound by per-warp dependent-issue latency with 2-3 warps per scheduler, not by instruction
-// count; a pathological slowdown on dense scenes besides).
+// count).
 #include "blend_common.cuh"
 
 namespace mgs {
