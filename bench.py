@@ -348,16 +348,45 @@ def make_e2e(impl_name, wl, torch):
     V = wl["views"]
     view_streams = None  # ours: render_views owns its per-view streams; the reference launches on the legacy default stream
 
+    pack_state = {}
+
+    def build_pack(Gh, Ch, Th):
+        """All tensors of one step (Gaussian parameters, camera matrices, cotangents) laid out in ONE pinned fp32 buffer,
+        every field on a 128-byte boundary: the step's H2D transfer is a single copy, the device tensors are views."""
+        fields = [("G", None, k, v) for k, v in Gh.items() if hasattr(v, "numel") and v.numel()]
+        fields += [("C", i, k, v) for i, ch in enumerate(Ch) for k, v in ch.items() if hasattr(v, "numel")]
+        fields += [("T", i, k, th[k]) for k in ("dL_dcolor", "dL_dfeature", "dL_ddepth") for i, th in enumerate(Th)
+                   if th.get(k) is not None]
+        offs, off = [], 0
+        for _, _, _, v in fields:
+            offs.append(off)
+            off += (v.numel() + 31) // 32 * 32
+        packed = torch.empty(off, dtype=torch.float32).pin_memory()
+        for (_, _, _, v), o in zip(fields, offs):
+            packed[o:o + v.numel()].copy_(v.reshape(-1))
+        pack_state.update(fields=fields, offs=offs, packed=packed)
+
     def upload(Gh, Ch, Th):
         """H2D copy of ONE step's inputs (pinned host -> device) on a copy stream, so that step i+1's inputs travel while
         step i computes (what a prefetching data loader does).  Returns the device tensors and a completion event."""
+        if not pack_state:
+            build_pack(Gh, Ch, Th)
         with torch.cuda.stream(copy_stream):
-            G = {k: (v.cuda(non_blocking=True) if v is not None and v.numel() else v) for k, v in Gh.items()}
-            C = [{k: (v.cuda(non_blocking=True) if hasattr(v, "cuda") else v) for k, v in ch.items()} for ch in Ch]
-            T = [{k: (v.cuda(non_blocking=True) if v is not None else None) for k, v in th.items()} for th in Th]
+            buf = pack_state["packed"].cuda(non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return G, C, T, ev
+        G = {k: v for k, v in Gh.items() if not (hasattr(v, "numel") and v.numel())}
+        C = [{k: v for k, v in ch.items() if not hasattr(v, "numel")} for ch in Ch]
+        T = [{k: None for k in th} for th in Th]
+        for (kind, i, k, v), o in zip(pack_state["fields"], pack_state["offs"]):
+            t = buf[o:o + v.numel()].view(v.shape)
+            if kind == "G":
+                G[k] = t
+            elif kind == "C":
+                C[i][k] = t
+            else:
+                T[i][k] = t
+        return G, C, T, ev, buf
 
     ring = [torch.zeros(1).pin_memory() for _ in range(2)]
     pending = []
@@ -390,15 +419,10 @@ def make_e2e(impl_name, wl, torch):
 
     def compute(dev):
         """render + loss + backward of every view through the autograd module, then D2H of the loss."""
-        G, C, T, ev = dev
+        G, C, T, ev, buf = dev
         main = torch.cuda.current_stream()
         main.wait_event(ev)
-        users = [main] + (view_streams or [])
-        for d in [G] + C + T:
-            for v in d.values():
-                if hasattr(v, "record_stream") and v.is_cuda:
-                    for u in users:
-                        v.record_stream(u)
+        buf.record_stream(main)  # allocated on the copy stream, consumed here (every input is a view of it)
         G = {k: (v.requires_grad_(True) if v is not None and v.numel() else v) for k, v in G.items()}
         if impl_name == "ours":
             # the public multi-view call: ONE autograd node for all views, gradients summed on the device

@@ -198,9 +198,18 @@ def render_views(cameras, pts_xyz, rotations, scales, opacity, bg_color=(0.0, 0.
         feat = normalize_features(features_language) if normalize_feature else features_language
     V, P = len(views), pts_xyz.shape[0]
     screenspace_points = torch.zeros((V, P, 3), dtype=torch.float32, device=device, requires_grad=True)
-    color, feat_img, radii, depth = _RasterizeViews.apply(
-        pts_xyz, screenspace_points, features_color, pts_rgb if features_color is None else None, feat, opacity, scales,
-        rotations, views, bool(return_depth), sync_gradients)
+    if V == 1 and sync_gradients is None:
+        # a single view needs neither side streams nor the packed accumulation buffer: the single-view operator is leaner
+        out = GaussianRasterizer(views[0], return_depth=return_depth)(
+            means3D=pts_xyz, means2D=screenspace_points[0], shs=features_color,
+            colors_precomp=pts_rgb if features_color is None else None, language_feature_precomp=feat, opacities=opacity,
+            scales=scales, rotations=rotations, cov3D_precomp=None)
+        color, feat_img, radii = out[0].unsqueeze(0), out[1].unsqueeze(0), out[2].unsqueeze(0)
+        depth = out[3].unsqueeze(0) if return_depth else None
+    else:
+        color, feat_img, radii, depth = _RasterizeViews.apply(
+            pts_xyz, screenspace_points, features_color, pts_rgb if features_color is None else None, feat, opacity, scales,
+            rotations, views, bool(return_depth), sync_gradients)
     ret = {"render": color, "render_embed": feat_img if include else None, "viewspace_points": screenspace_points,
            "radii": radii}
     if return_depth:

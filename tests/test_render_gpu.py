@@ -192,6 +192,14 @@ def test_render_views_equals_a_loop_of_render():
     o2 = render(data, 2, a["xyz"].detach(), a["rot"].detach(), a["scale"].detach(), a["opac"].detach(), [0.1, 0.2, 0.3], pts_rgb=rgb.detach())
     assert torch.equal(o2["render"], sub["render"][0])
     assert rgb.grad is not None and rgb.grad.abs().sum() > 0
+    # one view: the single-view operator underneath, same layout of the results
+    c = mk()
+    one = render_views(cams, c["xyz"], c["rot"], c["scale"], c["opac"], (0, 0, 0), features_color=c["sh"], features_language=c["feat"],
+                       view_ids=[3], return_depth=True)
+    assert one["render"].shape == (1, 3, H, W) and one["depth"].shape == (1, H, W) and one["radii"].shape == (1, P)
+    assert torch.equal(one["render"][0], outs["render"][3]) and torch.equal(one["render_embed"][0], outs["render_embed"][3])
+    ((one["render"][0] * cts[3][0]).sum() + (one["render_embed"][0] * cts[3][1]).sum() + (one["depth"][0] * cts[3][2]).sum()).backward()
+    assert util.rel_l2(one["viewspace_points"].grad[0].cpu().numpy(), vsp[3].cpu().numpy()) < 1e-5
 
 
 def test_dyna_step_end_to_end_gradients():
