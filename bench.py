@@ -341,7 +341,7 @@ def make_render(impl_name, wl, torch):
     return render, GaussianRasterizationSettings
 
 
-def make_e2e(impl_name, wl, torch):
+def make_e2e(impl_name, wl, torch, dist=None):
     P, F = wl["P"], wl["F"]
     render, GaussianRasterizationSettings = make_render(impl_name, wl, torch)
     copy_stream = torch.cuda.Stream()
@@ -430,7 +430,8 @@ def make_e2e(impl_name, wl, torch):
             views = [GaussianRasterizationSettings(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], cam["bg"], 1.0, cam["viewmatrix"],
                                                    cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, F > 0) for cam in C]
             o = render_views(views, G["means3D"], G["rotations"], G["scales"], G["opacities"], features_color=G["shs"],
-                             features_language=G["feature"] if F else None, return_depth=wl["depth"], normalize_feature=False)
+                             features_language=G["feature"] if F else None, return_depth=wl["depth"], normalize_feature=False,
+                             sync_gradients=True if dist is not None else None)  # N > 1: the one all-reduce, inside the backward
             loss = (o["render"] * torch.stack([ct["dL_dcolor"] for ct in T])).sum()
             if F:
                 loss = loss + (o["render_embed"] * torch.stack([ct["dL_dfeature"] for ct in T])).sum()
@@ -455,6 +456,10 @@ def make_e2e(impl_name, wl, torch):
         for lv in losses[1:]:
             loss = loss + lv
         loss.backward()
+        if dist is not None:  # N > 1: the reference has no packed buffer; its per-Gaussian gradients are summed field by field
+            for v in G.values():
+                if getattr(v, "grad", None) is not None:
+                    dist.all_reduce(v.grad)
         return read_back(loss)
 
     def step(Gh, Ch, Th, state):
@@ -816,7 +821,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         Gh, Ch, Th = to_device(g, cams, cts, torch, pinned=True)
-        step = make_e2e(a.impl, wl, torch)
+        step = make_e2e(a.impl, wl, torch, dist)
         e2e_state = {}
         for _ in range(max(3, a.warmup)):
             step(Gh, Ch, Th, e2e_state)
