@@ -1,0 +1,68 @@
+"""Host-side logic of the layers around the rasterizer (rows f1-f3) that needs no GPU: argument checking, the reference's
+call signatures, error codes of the pre-op entry points, and the refusal to run on CPU tensors (no fallback)."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+import util  # noqa: F401  (sys.path)
+from manigaussian_b200 import _binding, cameras, gaussian_params, gaussian_renderer
+
+
+def test_render_keeps_the_reference_signature():
+    """agents/manigaussian_bc/gaussian_renderer/__init__.py:17: render(data, idx, pts_xyz, rotations, scales, opacity,
+    bg_color, pts_rgb=None, features_color=None, features_language=None); ours only appends optional arguments."""
+    params = list(inspect.signature(gaussian_renderer.render).parameters)
+    assert params[:10] == ["data", "idx", "pts_xyz", "rotations", "scales", "opacity", "bg_color", "pts_rgb", "features_color",
+                           "features_language"]
+    sig = inspect.signature(gaussian_renderer.render)
+    assert all(sig.parameters[p].default is None for p in ("pts_rgb", "features_color", "features_language"))
+
+
+def test_no_cpu_fallback_in_the_new_layers():
+    P = 8
+    z = lambda *s: torch.zeros(*s)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gaussian_params.activate_gaussians(z(P, 3), z(P, 4), z(P, 3), z(P, 1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gaussian_renderer.normalize_features(torch.ones(P, 4))
+    cb = cameras.build_cameras(np.tile(np.array([[100., 0, 32], [0, 100., 32], [0, 0, 1]]), (2, 1, 1)),
+                               np.tile(np.eye(4), (2, 1, 1)), 64, 64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gaussian_renderer.render_views(cb, z(P, 3), z(P, 4), z(P, 3), z(P, 1), pts_rgb=z(P, 3))
+
+
+def test_argument_checks():
+    P = 4
+    z = lambda *s: torch.zeros(*s)
+    with pytest.raises(ValueError):
+        gaussian_params.activate_gaussians(z(P, 3), z(P, 4), z(P, 3), z(P), opacity_activation="tanh")
+    cb = cameras.build_cameras(np.array([[100., 0, 32], [0, 100., 32], [0, 0, 1]]), np.eye(4), 64, 64)
+    with pytest.raises(ValueError):  # neither SH nor precomputed colours (the reference's exception text is kept)
+        gaussian_renderer.render_views(cb, z(P, 3), z(P, 4), z(P, 3), z(P, 1))
+    with pytest.raises(ValueError):
+        gaussian_renderer.render_views(cb, z(P, 3), z(P, 4), z(P, 3), z(P, 1), pts_rgb=z(P, 3), view_ids=[])
+
+
+def test_pre_op_entry_points_reject_bad_arguments_without_a_gpu():
+    L = _binding.lib()
+    assert L.mgs_activate(-1, 0, *([None] * 8), 0, 0.05, 0, 0, 0, *([None] * 6)) < 0
+    assert L.mgs_activate(4, 0, *([None] * 8), 7, 0.05, 0, 0, 0, *([None] * 6)) < 0 and "mode" in _binding.last_error()
+    assert L.mgs_activate(0, 0, *([None] * 8), 1, 0.05, 1, 1, 1, *([None] * 6)) == 0          # empty cloud: nothing to do
+    assert L.mgs_activate_backward(0, 0, *([None] * 8), 1, 0.05, 1, 1, 1, *([None] * 14)) == 0
+    # an output requested for an input that is NULL
+    assert L.mgs_activate(4, 0, *([None] * 8), 0, 0.05, 0, 0, 0, 4096, None, None, None, None, None) < 0
+
+
+def test_camera_batch_is_host_resident():
+    K = np.array([[120., 0, 40], [0, 110., 30], [0, 0, 1]])
+    cb = cameras.build_cameras(np.stack([K, K]), np.stack([np.eye(4), np.eye(4)]), 80, 60)
+    nv = cb.as_novel_view()
+    s = gaussian_renderer._camera_scalars(nv, 1)
+    assert s == (cb.tanfovx[1], cb.tanfovy[1], 60, 80)            # no tensor reads: host scalars
+    assert cb.world_view_transform.shape == (2, 4, 4) and cb.camera_center.shape == (2, 3)
+    assert cameras.focal2fov(120.0, 80) == pytest.approx(2 * np.arctan(80 / 240.0))
+    # identity pose: world->view is the identity, the camera sits at the origin
+    np.testing.assert_allclose(cb.host["world_view_transform"][0], np.eye(4), atol=1e-7)
+    np.testing.assert_allclose(cb.host["camera_center"][0], 0, atol=1e-7)
