@@ -40,6 +40,9 @@ constexpr int QCAP = 64;  // survivor queue capacity (power of two, >= 63)
 #ifndef MGS_BWD_PIX
 #define MGS_BWD_PIX 2
 #endif
+#ifndef MGS_BWD_PREDICATED
+#define MGS_BWD_PREDICATED 0
+#endif
 constexpr int PIX = MGS_BWD_PIX;  // pixels interleaved per iteration of the pixel walk (instruction-level parallelism)
 #ifdef MGS_BWD_MIN_CTAS
 constexpr int BWD_MIN_CTAS = MGS_BWD_MIN_CTAS;
@@ -228,6 +231,24 @@ __global__ void __launch_bounds__(32, BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a
 				const float Tnew = __shfl_sync(0xffffffffu, Tk[u], 31);
 				const float Snew = st[u].y + __shfl_sync(0xffffffffu, is[u], 31);
 				if (lane == 0) s_state[p + u] = make_float4(Tnew, Snew, st[u].z, st[u].w);
+#if MGS_BWD_PREDICATED
+				// EXPERIMENT (off; not yet measured on a GPU): ~10 of 32 lanes are valid here on the benchmark cloud, so the
+				// divergent region below costs a reconvergence per pixel; this form computes the addends on every lane and
+				// selects them away on lanes that are not valid (a select, not a multiply: G can be inf where power > 0).
+				{
+					const float dL_dalpha = Tk[u] * w[u] - __fdividef(Sk + st[u].w, 1.f - alpha[u]);
+					const float dL_dG = op * dL_dalpha;
+					const float gdx = G[u] * dx[u], gdy = G[u] * dy[u];
+					const float dG_ddelx = -gdx * ca - gdy * cb;
+					const float dG_ddely = -gdy * cc - gdx * cb;
+					dmx += valid[u] ? dL_dG * dG_ddelx * ddelx_dx : 0.f;
+					dmy += valid[u] ? dL_dG * dG_ddely * ddely_dy : 0.f;
+					dca += valid[u] ? -0.5f * gdx * dx[u] * dL_dG : 0.f;
+					dcb += valid[u] ? -0.5f * gdx * dy[u] * dL_dG : 0.f;
+					dcc += valid[u] ? -0.5f * gdy * dy[u] * dL_dG : 0.f;
+					dop += valid[u] ? G[u] * dL_dalpha : 0.f;
+				}
+#else
 				if (valid[u]) {
 					const float dL_dalpha = Tk[u] * w[u] - __fdividef(Sk + st[u].w, 1.f - alpha[u]);
 					const float dL_dG = op * dL_dalpha;
@@ -241,6 +262,7 @@ __global__ void __launch_bounds__(32, BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a
 					dcc += -0.5f * gdy * dy[u] * dL_dG;
 					dop += G[u] * dL_dalpha;
 				}
+#endif
 			}
 		}
 		__syncwarp();

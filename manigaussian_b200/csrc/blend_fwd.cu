@@ -28,6 +28,10 @@
 // count).
 #include "blend_common.cuh"
 
+#ifndef MGS_FWD_PREDICATED
+#define MGS_FWD_PREDICATED 0
+#endif
+
 namespace mgs {
 
 template <int NQ, bool VEC>
@@ -123,6 +127,32 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 			const float4* rows = s_rows[rb];
 			const uint32_t pos0 = (uint32_t)(g * 32) + 1u;  // 1-based position of the chunk's first record in the tile list
 			// two survivors per step (see the header)
+#if MGS_FWD_PREDICATED
+			// EXPERIMENT (off; not yet measured on a GPU): the SASS view of the round-1 capture puts ~25 % of this kernel's
+			// stall samples on the divergent skip tests (BRA wait + branch_resolving after each BSYNC).  Here the per-lane
+			// decisions become selects, the channel FMAs run for the whole warp behind ONE warp-uniform branch with w = 0 on
+			// lanes that do not contribute (fma(v, 0, acc) == acc for finite v), and the two survivors of a step can
+			// interleave freely.  Differs from the committed walk only for non-finite channel values.
+			auto blend_one = [&](bool act, int b, float power, float alpha_raw, const float4* row) {
+				const float alpha = min(ALPHA_MAX, alpha_raw);
+				const bool cand = act && !done && !(power > 0.0f) && !(alpha < ALPHA_MIN);
+				const float test_T = T * (1 - alpha);
+				const bool stop = cand && (test_T < T_STOP);
+				const bool use = cand && !stop;
+				done = done || stop;
+				if (__any_sync(0xffffffffu, use)) {
+					const float w = use ? alpha * T : 0.f;
+#pragma unroll
+					for (int q = 0; q < NQ; q++) {
+						const float4 v = row[q];
+						acc[4 * q + 0] += v.x * w; acc[4 * q + 1] += v.y * w;
+						acc[4 * q + 2] += v.z * w; acc[4 * q + 3] += v.w * w;
+					}
+				}
+				T = use ? test_T : T;
+				last_contributor = use ? pos0 + (uint32_t)b : last_contributor;
+			};
+#else
 			auto blend_one = [&](int b, float power, float alpha_raw, const float4* row) {
 				if (done || power > 0.0f) return;
 				const float alpha = min(ALPHA_MAX, alpha_raw);
@@ -139,6 +169,7 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 				T = test_T;
 				last_contributor = pos0 + (uint32_t)b;
 			};
+#endif
 			int i = 0;
 			uint32_t mask = mask_cur;
 			while (mask) {
@@ -154,8 +185,13 @@ __global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
 				const float power1 = -0.5f * (p1.z * dx1 * dx1 + q1.x * dy1 * dy1) - p1.w * dx1 * dy1;
 				const float a0 = q0.y * expf(power0);
 				const float a1 = q1.y * expf(power1);
+#if MGS_FWD_PREDICATED
+				blend_one(true, b0, power0, a0, rows + i * NQ);
+				blend_one(two, b1, power1, a1, rows + (i + 1) * NQ);
+#else
 				blend_one(b0, power0, a0, rows + i * NQ);
 				if (two) blend_one(b1, power1, a1, rows + (i + 1) * NQ);
+#endif
 				i += two ? 2 : 1;
 			}
 		}
