@@ -1,16 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- Gaussians/s fwd+bwd of the rasterizer hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|cpu] [--workload c1|c2|c3|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|cpu] [--workload c1|c2|c3|c4|c5|mg]
 
 A "step" = forward + backward of every view of the workload over one synthetic Gaussian cloud:
 default workload c3 = BASELINE.json configs[2]: 500k Gaussians, 4 views 256x256, RGB + 32 feature channels.
 One JSON line is printed by rank 0.  Keys are described in DESIGN.md ("Measurement").
 
   value      whole-job Gaussians/s (P * views / s), inputs resident in HBM, through the C ABI (raw calls)
-  e2e        same metric through the public nn.Module/autograd API with pinned-host inputs copied H2D every step
-             and a scalar read back D2H
-  roofline   dominant kernel (backward blend): algorithmic bytes / CUDA-event time vs measured HBM peak
+  e2e        same metric through the public autograd API (ours: gaussian_renderer.render_views) with the step's inputs
+             copied pinned-host -> device every step (one packed copy) and the loss read back D2H every step
+  roofline   dominant kernel (backward blend; on c4 the HBM-bound pre-op kernels): algorithmic bytes / CUDA-event time
+             vs the measured HBM peak
   cpu_baseline  the CPU oracle (oracle/gs_oracle.c, OpenMP) timed on a bounded sample of the same workload
 
 --impl reference times the UNMODIFIED reference rasterizer compiled for sm_100 (oracle/_ref, built by
