@@ -66,3 +66,22 @@ def test_camera_batch_is_host_resident():
     # identity pose: world->view is the identity, the camera sits at the origin
     np.testing.assert_allclose(cb.host["world_view_transform"][0], np.eye(4), atol=1e-7)
     np.testing.assert_allclose(cb.host["camera_center"][0], 0, atol=1e-7)
+
+
+def test_packed_gradient_buffer_layout():
+    """One flat message for the all-reduce; every field starts on a 16-byte boundary (128-bit reductions target it) and the
+    optional precomputed-colour field only exists when asked for."""
+    from manigaussian_b200.parallel import FIELDS, PackedGradients, shard_views
+    P, F, M = 1001, 32, 4   # odd P: field sizes are not multiples of four floats
+    pk = PackedGradients(P, F, M, "cpu")
+    base = pk.flat.data_ptr()
+    for k, v in pk.views.items():
+        assert (v.data_ptr() - base) % 16 == 0, k
+        assert v.shape == (P, pk.widths[k]) and v.is_contiguous()
+    assert "dL_dcolors" not in pk.views and set(pk.views) <= set(FIELDS)
+    assert pk.bytes_per_gaussian == 4 * (3 + 3 + 3 + 4 + 1 + 3 * M + F)
+    assert "dL_dcolors" in PackedGradients(P, 0, 0, "cpu", colors=True).views
+    # fields do not overlap
+    spans = sorted((v.data_ptr(), v.data_ptr() + v.numel() * 4) for v in pk.views.values())
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    assert sorted(shard_views(8, 0, 4) + shard_views(8, 1, 4) + shard_views(8, 2, 4) + shard_views(8, 3, 4)) == list(range(8))
