@@ -10,7 +10,7 @@
 // to the raw parameters and to the offsets in one pass.  HBM-bound streaming kernels: each input/output float moves once.
 //
 // Arithmetic mirrors the PyTorch operators (IEEE division, expf, sqrtf); reductions over a row run in a different
-// order than ATen's, so results agree to an ulp or two, not bit for bit (tests/test_activate_gpu.py states 1e-6).
+// order than ATen's, so results agree to an ulp or two, not bit for bit (tests/test_render_gpu.py::test_fused_activations_match_torch_golden_and_oracle states 2e-6).
 #include "mgs_common.cuh"
 #include "mgs_kernels.h"
 

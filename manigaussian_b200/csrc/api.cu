@@ -4,6 +4,7 @@
 // (DGR/cuda_rasterizer/rasterizer_impl.cu:198-355, :359-463, :141-153).  Stage order and the meaning of
 // every argument follow the reference; the state-buffer layout, kernels and stream handling are ours.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <map>
@@ -148,6 +149,15 @@ static size_t required(F carve)
 	char* p = nullptr;
 	carve(p);
 	return reinterpret_cast<size_t>(p) + 128;
+}
+int blend_variant()
+{
+	static const int v = [] {
+		const char* e = getenv("MGS_BLEND");
+		const std::string s = e ? e : "";
+		return s == "simt" ? 3 : s == "simt_fwd" ? 1 : s == "simt_bwd" ? 2 : 0;
+	}();
+	return v;
 }
 static size_t num_tiles(int W, int H) { return (size_t)ceil_div(W, TILE_X) * ceil_div(H, TILE_Y); }
 

@@ -13,7 +13,7 @@
 
 namespace mgs {
 
-constexpr int REC_BATCH = 64;  // records per bulk copy (2 KB) = two 32-record chunks
+constexpr int REC_BATCH = 64;  // records per bulk copy of the round-1 SIMT kernels (2 KB) = two 32-record chunks
 #ifndef MGS_RING
 #define MGS_RING 2
 #endif
@@ -39,17 +39,18 @@ __device__ __forceinline__ bool rec_hits_block(const float4& r0, const float4& r
 	return (e.x >= 0.f) && (r0.x + e.x >= x0) && (r0.x - e.x <= x1) && (r0.y + e.y >= y0) && (r0.y - e.y <= y1);
 }
 
-// Per-warp record ring.  All methods are called by the whole (converged) warp.
-struct WarpRecRing {
-	InstRec* buf;        // RING * REC_BATCH records
+// Per-warp record ring of BATCH-record buffers.  All methods are called by the whole (converged) warp.
+template <int BATCH>
+struct WarpRecRingT {
+	InstRec* buf;        // RING * BATCH records
 	uint64_t* bar;       // RING mbarriers (count 1)
 	const InstRec* src;  // first record of the (sub)list this warp walks
 	int total;           // number of records to walk
-	bool reverse;        // walk from the back (backward pass): batch 0 is the LAST REC_BATCH-aligned block
+	bool reverse;        // walk from the back (backward pass): batch 0 is the LAST BATCH-aligned block
 
-	__device__ __forceinline__ int num_batches() const { return (total + REC_BATCH - 1) / REC_BATCH; }
-	__device__ __forceinline__ int batch_lo(int k) const { return reverse ? REC_BATCH * (num_batches() - 1 - k) : REC_BATCH * k; }
-	__device__ __forceinline__ int batch_n(int k) const { return min(REC_BATCH, total - batch_lo(k)); }
+	__device__ __forceinline__ int num_batches() const { return (total + BATCH - 1) / BATCH; }
+	__device__ __forceinline__ int batch_lo(int k) const { return reverse ? BATCH * (num_batches() - 1 - k) : BATCH * k; }
+	__device__ __forceinline__ int batch_n(int k) const { return min(BATCH, total - batch_lo(k)); }
 
 	__device__ __forceinline__ void init(InstRec* b, uint64_t* bars, const InstRec* s, int n, bool rev)
 	{
@@ -69,16 +70,17 @@ struct WarpRecRing {
 			const int b = k % RING, n = batch_n(k);
 			fence_proxy_async();
 			mbar_arrive_expect_tx(&bar[b], (uint32_t)n * (uint32_t)sizeof(InstRec));
-			bulk_g2s(buf + b * REC_BATCH, src + batch_lo(k), (uint32_t)n * (uint32_t)sizeof(InstRec), &bar[b]);
+			bulk_g2s(buf + b * BATCH, src + batch_lo(k), (uint32_t)n * (uint32_t)sizeof(InstRec), &bar[b]);
 		}
 	}
 	__device__ __forceinline__ const float4* wait(int k)
 	{
 		const int b = k % RING;
 		mbar_wait(&bar[b], (uint32_t)((k / RING) & 1));
-		return reinterpret_cast<const float4*>(buf + b * REC_BATCH);
+		return reinterpret_cast<const float4*>(buf + b * BATCH);
 	}
-	__device__ __forceinline__ const float4* buffer(int k) const { return reinterpret_cast<const float4*>(buf + (k % RING) * REC_BATCH); }
+	__device__ __forceinline__ const float4* buffer(int k) const { return reinterpret_cast<const float4*>(buf + (k % RING) * BATCH); }
 };
+using WarpRecRing = WarpRecRingT<REC_BATCH>;
 
 }  // namespace mgs

@@ -5,260 +5,295 @@
 // when T*(1-alpha) < 1e-4, colour gets + T*bg, features/depth do not; final_T and n_contrib saved).
 //
 // B200 design (not the reference's; see blend_common.cuh for the decomposition):
-//  * one single-warp CTA per 8x4 pixel block; the warp culls its tile's work list against the block with the
-//    per-Gaussian alpha >= 1/255 footprint (exact-conservative; decided by ballot), so a pixel only evaluates
-//    Gaussians that can reach its block (about a third of the tile's list on the benchmark workload);
-//  * two-level software pipeline, all data movement asynchronous:
-//      records     : RING 64-record batches in flight/resident, one contiguous 1-D TMA bulk copy each (UBLKCP + mbarrier);
-//      channel rows: while chunk g is blended, the {r,g,b,depth} quad and the F-float feature row of every SURVIVOR of
-//                    chunk g+1 are gathered by Gaussian id into a double-buffered row array with 16-byte cp.async
-//                    (LDGSTS) pieces spread over the lanes, one commit group per chunk.  (A bulk copy per survivor was
-//                    the first design; UBLKCP takes uniform operands, so the compiler serialised it into a loop trip per
-//                    survivor and copy -- 15 % of the kernel's stall samples.  LDGSTS: 0.426 -> 0.374 ms per c3 view.)
-//  * channel rows are consumed from shared memory as 128-bit broadcasts instead of per-pair scalar global
-//    gathers (forward.cu:364-371);
-//  * feature width is a run-time value dispatched to NQ = ceil((4+F)/4) in {1,2,3,5,9};
-//  * two survivors are evaluated per step of the walk: their footprint evaluations are independent of the transmittance
-//    recurrence, so the second one's expf latency overlaps with the first one's channel FMAs.
-// Tried and rejected on B200 (all bit-identical; numbers per c3 view, this kernel 0.427 ms): "sub-block lockstep" (lanes of
-// the two 4x4 halves walk their own survivor lists in lockstep: 25 % fewer steps, 0.443 ms -- the per-lane bookkeeping
-// costs what the steps save) and a two-phase walk (phase A evaluates alpha for all survivors into shared memory, phase B
-// lets every lane blend only its own contributors: ncu shows 7 of 32 threads active in the channel FMAs here, yet
-// 0.429 ms -- the walk is bound by per-warp dependent-issue latency with 2-3 warps per scheduler, not by instruction
-// count).
+//  * one single-warp CTA per 8x4 pixel block; the warp streams its tile's sorted records through a ring of 1-D TMA
+//    bulk copies, culls every 32-record chunk against the block with the per-Gaussian alpha >= 1/255 footprint
+//    (exact-conservative, one ballot) and QUEUES the survivors in shared memory;
+//  * whenever FWD_CH survivors are queued the warp runs one chunk in two phases:
+//      walk       lane = pixel, sequential over the chunk's survivors: the exact transmittance recurrence of the
+//                 reference (same expf, same skip/stop tests, so final_T and n_contrib agree bit for bit); instead of
+//                 36 channel FMAs per survivor (7 of 32 lanes active on the benchmark cloud) the lane only stores its
+//                 blend weight w = alpha*T (0 when the pair does not contribute) into a [survivor][pixel] tile;
+//      contract   acc[pixel][channel] += W[pixel][survivor] * C[survivor][channel] on the tensor cores (mma.sync
+//                 m16n8k8 TF32, 3xTF32 split for fp32 accuracy, blend_mma.cuh), accumulators in the D fragments;
+//    the channel rows C of the chunk ({r,g,b,depth} quad + feature row, gathered by Gaussian id with 16-byte cp.async
+//    pieces, SASS LDGSTS) travel while the walk runs;
+//  * index assignment that makes every fragment access wide and conflict free: MMA row 16 mt + 8 h + gid is pixel
+//    (x = gid, y = 2 mt + h) = lane 4 gid + y of the walk, so a thread's four A values per survivor are one LDS.128 of
+//    the XOR-swizzled weight tile; column gid of feature tile nt is feature NFT*gid + nt, so a thread's B values per
+//    survivor are one LDS.128 of the channel row and its D fragments hold 2*NFT consecutive features of four pixels;
+//    with x = gid the output planes are written as full 32-byte sectors straight from the fragments.
 #include "blend_common.cuh"
-
-#ifndef MGS_FWD_PREDICATED
-#define MGS_FWD_PREDICATED 0
-#endif
+#include "blend_mma.cuh"
 
 namespace mgs {
 
-template <int NQ, bool VEC>
-__global__ void __launch_bounds__(32, 16) blend_fwd_kernel(BlendArgs a)
+#ifndef MGS_FWD_CH
+#define MGS_FWD_CH 32
+#endif
+#ifndef MGS_FWD_MIN_CTAS
+#define MGS_FWD_MIN_CTAS 16
+#endif
+#ifndef MGS_FWD_BATCH
+#define MGS_FWD_BATCH 32
+#endif
+constexpr int FWD_CH = MGS_FWD_CH;        // survivors per tensor-core chunk (multiple of 8, <= 32)
+constexpr int FWD_QCAP = FWD_CH + 32;     // survivor queue: a chunk plus the survivors of one more 32-record cull
+constexpr int FWD_BATCH = MGS_FWD_BATCH;  // records per bulk copy (a multiple of the 32-record cull chunk)
+static_assert(FWD_CH % 8 == 0 && FWD_CH <= 32 && FWD_BATCH % 32 == 0, "forward chunk size");
+
+template <int NFT, bool VEC>
+__global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendArgs a)
 {
-	__shared__ __align__(128) InstRec s_rec[RING * REC_BATCH];
-	__shared__ __align__(16) float4 s_rows[2][32 * NQ];
-	__shared__ __align__(8) uint64_t s_bar_rec[RING];
-	__shared__ uint32_t s_ids[32];  // Gaussian ids of the chunk's survivors by rank (row gather addressing)
+	using L = RowLayout<NFT>;
+	constexpr int RS = L::RS;
+	constexpr int NT = NFT + 1;  // column tiles: NFT feature tiles + the {r,g,b,depth} tile
+	__shared__ __align__(128) InstRec s_rec[RING * FWD_BATCH];
+	__shared__ __align__(16) float4 s_q[FWD_QCAP * 2];    // survivor queue, linear: {x,y,ca,cb}, {cc,op,pos,id}; the chunk is its head
+	__shared__ __align__(16) float s_rows[FWD_CH * RS];   // channel rows of the current chunk
+	__shared__ __align__(16) float s_w[FWD_CH * 32];      // blend weights [survivor][pixel ^ 8 (survivor & 3)]
+	__shared__ __align__(8) uint64_t s_bar[RING];
 
 	const int lane = threadIdx.x;
+	const int gid = lane >> 2, tig = lane & 3;
 	const int tile = blockIdx.x >> 3, sub = blockIdx.x & 7;
 	const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
 	const int bx0 = tile_x * TILE_X + (sub & 1) * WARP_BX;
 	const int by0 = tile_y * TILE_Y + (sub >> 1) * WARP_BY;
-	const int pxi = bx0 + (lane & 7), pyi = by0 + (lane >> 3);
+	// walk role: lane = pixel (x = lane >> 2, y = lane & 3)
+	const int pxi = bx0 + (lane >> 2), pyi = by0 + (lane & 3);
 	const bool inside = pxi < a.W && pyi < a.H;
 	if (__all_sync(0xffffffffu, !inside)) return;  // block entirely outside the image (ragged right/bottom tiles)
 	const float pfx = (float)pxi, pfy = (float)pyi;
 	const float fbx0 = (float)bx0, fbx1 = (float)(bx0 + WARP_BX - 1), fby0 = (float)by0, fby1 = (float)(by0 + WARP_BY - 1);
 	const int F = a.F;
 
+	// rows beyond a short last chunk are multiplied by zero weights: they must hold finite numbers
+	for (int i = lane; i < FWD_CH * RS / 4; i += 32) reinterpret_cast<float4*>(s_rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
 	const uint2 range = a.ranges[tile];
-	WarpRecRing ring;
-	ring.init(s_rec, s_bar_rec, a.recs + range.x, (int)(range.y - range.x), false);
+	WarpRecRingT<FWD_BATCH> ring;
+	ring.init(s_rec, s_bar, a.recs + range.x, (int)(range.y - range.x), false);
 	const int nb = ring.num_batches();
-	const int nchunks = (ring.total + 31) >> 5;
-	int issued = 0, waited = 0;      // record batches
+	int issued = 0, waited = 0;
+	for (; issued < min(nb, RING); issued++) ring.issue(issued);
 
 	float T = 1.0f;
 	uint32_t last_contributor = 0;
 	bool done = !inside;
-	float acc[4 * NQ];
+	float acc[2][NT][4];
 #pragma unroll
-	for (int i = 0; i < 4 * NQ; i++) acc[i] = 0.f;
+	for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+		for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+			for (int i = 0; i < 4; i++) acc[mt][nt][i] = 0.f;
 
-	// cull chunk g and start gathering the survivors' channel rows into s_rows[g & 1]
-	auto prefetch_chunk = [&](int g) -> uint32_t {
-		const int k = g >> 1;
-		if ((g & 1) == 0) { ring.wait(k); waited = k + 1; }
-		__syncwarp();
-		const float4* rec4 = ring.buffer(k);
-		const int j = ((g & 1) << 5) + lane;
-		const bool hit = (g * 32 + lane < ring.total) && rec_hits_block(rec4[2 * j], rec4[2 * j + 1], fbx0, fbx1, fby0, fby1);
-		const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-		if (mask) {
-			float4* rows = s_rows[g & 1];
-			const int rank = __popc(mask & ((1u << lane) - 1u));
-			if (VEC) {
-				// cooperative gather: the rows of all survivors are cut into 16-byte pieces and every lane copies pieces
-				// lane, lane+32, ... with per-lane addresses (LDGSTS).  A per-survivor bulk copy (UBLKCP) takes uniform
-				// operands, so the compiler serialises it into one loop trip per survivor and copy.
-				if (hit) s_ids[rank] = rec_id(rec4[2 * j + 1]);
-				__syncwarp();
-				const int npieces = __popc(mask) * NQ;
-				for (int idx = lane; idx < npieces; idx += 32) {
-					const int r = idx / NQ, q = idx - r * NQ;
-					const uint32_t id = s_ids[r];
-					const float4* src = (q == 0) ? (a.rgbd + id) : (reinterpret_cast<const float4*>(a.feature + (size_t)id * F) + (q - 1));
-					cp_async16(rows + idx, src);
-				}
-			} else if (hit) {  // rows that are not 16-byte multiples (e.g. F = 3): plain loads
-				const uint32_t id = rec_id(rec4[2 * j + 1]);
-				rows[rank * NQ] = a.rgbd[id];
-				if (NQ > 1) {
-					float* rf = reinterpret_cast<float*>(rows + rank * NQ + 1);
-					const float* f = a.feature + (size_t)id * F;
-#pragma unroll
-					for (int i = 0; i < 4 * (NQ - 1); i++) rf[i] = (i < F) ? f[i] : 0.f;
-				}
-			}
-		}
-		if (VEC) cp_async_commit();  // one group per prefetched chunk, empty or not: wait_group counts stay uniform
-		return mask;
+	int qcount = 0;
+	const int lsw0 = lane, lsw1 = lane ^ 8, lsw2 = lane ^ 16, lsw3 = lane ^ 24;  // pixel column of the swizzled weight tile, by survivor & 3
+
+	// one survivor of the walk: returns this pixel's blend weight
+	auto blend_step = [&](bool act, const float4& p, const float4& q) -> float {
+		const float dx = p.x - pfx, dy = p.y - pfy;
+		const float power = -0.5f * (p.z * dx * dx + q.x * dy * dy) - p.w * dx * dy;
+		const float alpha = min(ALPHA_MAX, q.y * expf(power));
+		const bool cand = act && !done && !(power > 0.0f) && !(alpha < ALPHA_MIN);
+		const float test_T = T * (1 - alpha);
+		const bool stop = cand && (test_T < T_STOP);
+		const bool use = cand && !stop;
+		const float w = use ? alpha * T : 0.f;
+		done = done || stop;
+		T = use ? test_T : T;
+		last_contributor = use ? __float_as_uint(q.z) : last_contributor;
+		return w;
 	};
 
-	uint32_t mask_cur = 0, mask_next = 0;
-	if (nchunks > 0) {
-		for (; issued < min(nb, RING); issued++) ring.issue(issued);
-		mask_cur = prefetch_chunk(0);
-	}
-	for (int g = 0; g < nchunks; g++) {
-		mask_next = 0;
-		if (g + 1 < nchunks) mask_next = prefetch_chunk(g + 1);
-		if (mask_cur) {
-			const int rb = g & 1;
-			if (VEC) {
-				// groups complete in order: all but the newest one (chunk g+1, if it was prefetched) must have landed
-				if (g + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
+	// consume the first cnt (<= FWD_CH) queued survivors; returns true when every pixel of the block is finished
+	auto process_chunk = [&](int cnt) -> bool {
+		// ---- start the gather of the chunk's channel rows (lands while the walk runs) ----
+		if (VEC) {
+			constexpr int NPR = 2 * NFT + 1;  // 16-byte pieces per row: feature pieces, then {r,g,b,depth} at 4*(2 NFT) = L::RGBD
+			const int npieces = cnt * NPR;
+			for (int idx = lane; idx < npieces; idx += 32) {
+				const int r = idx / NPR, q = idx - r * NPR;
+				const uint32_t id = __float_as_uint(s_q[2 * r + 1].w);
+				const float4* src = (q == 2 * NFT) ? (a.rgbd + id) : (reinterpret_cast<const float4*>(a.feature + (size_t)id * F) + q);
+				cp_async16(s_rows + r * RS + 4 * q, src);
 			}
-			__syncwarp();
-			const float4* rec4 = ring.buffer(g >> 1) + (rb << 6);
-			const float4* rows = s_rows[rb];
-			const uint32_t pos0 = (uint32_t)(g * 32) + 1u;  // 1-based position of the chunk's first record in the tile list
-			// two survivors per step (see the header)
-#if MGS_FWD_PREDICATED
-			// EXPERIMENT (off; not yet measured on a GPU): the SASS view of the round-1 capture puts ~25 % of this kernel's
-			// stall samples on the divergent skip tests (BRA wait + branch_resolving after each BSYNC).  Here the per-lane
-			// decisions become selects, the channel FMAs run for the whole warp behind ONE warp-uniform branch with w = 0 on
-			// lanes that do not contribute (fma(v, 0, acc) == acc for finite v), and the two survivors of a step can
-			// interleave freely.  Differs from the committed walk only for non-finite channel values.
-			auto blend_one = [&](bool act, int b, float power, float alpha_raw, const float4* row) {
-				const float alpha = min(ALPHA_MAX, alpha_raw);
-				const bool cand = act && !done && !(power > 0.0f) && !(alpha < ALPHA_MIN);
-				const float test_T = T * (1 - alpha);
-				const bool stop = cand && (test_T < T_STOP);
-				const bool use = cand && !stop;
-				done = done || stop;
-				if (__any_sync(0xffffffffu, use)) {
-					const float w = use ? alpha * T : 0.f;
+			cp_async_commit();
+		} else if (lane < cnt) {  // feature rows that are not whole 8-wide tiles (e.g. F = 3): plain loads, zero padded
+			const uint32_t id = __float_as_uint(s_q[2 * lane + 1].w);
+			float* row = s_rows + lane * RS;
+			*reinterpret_cast<float4*>(row + L::RGBD) = a.rgbd[id];
+			if (NFT > 0) {
+				const float* f = a.feature + (size_t)id * F;
 #pragma unroll
-					for (int q = 0; q < NQ; q++) {
-						const float4 v = row[q];
-						acc[4 * q + 0] += v.x * w; acc[4 * q + 1] += v.y * w;
-						acc[4 * q + 2] += v.z * w; acc[4 * q + 3] += v.w * w;
-					}
-				}
-				T = use ? test_T : T;
-				last_contributor = use ? pos0 + (uint32_t)b : last_contributor;
-			};
-#else
-			auto blend_one = [&](int b, float power, float alpha_raw, const float4* row) {
-				if (done || power > 0.0f) return;
-				const float alpha = min(ALPHA_MAX, alpha_raw);
-				if (alpha < ALPHA_MIN) return;
-				const float test_T = T * (1 - alpha);
-				if (test_T < T_STOP) { done = true; return; }
-				const float w = alpha * T;
-#pragma unroll
-				for (int q = 0; q < NQ; q++) {
-					const float4 v = row[q];
-					acc[4 * q + 0] += v.x * w; acc[4 * q + 1] += v.y * w;
-					acc[4 * q + 2] += v.z * w; acc[4 * q + 3] += v.w * w;
-				}
-				T = test_T;
-				last_contributor = pos0 + (uint32_t)b;
-			};
-#endif
-			int i = 0;
-			uint32_t mask = mask_cur;
-			while (mask) {
-				const int b0 = __ffs(mask) - 1;
-				mask &= mask - 1;
-				const bool two = mask != 0;
-				const int b1 = two ? __ffs(mask) - 1 : b0;
-				if (two) mask &= mask - 1;
-				const float4 p0 = rec4[2 * b0], q0 = rec4[2 * b0 + 1];  // {x, y, ca, cb}, {cc, op, ext, id}
-				const float4 p1 = rec4[2 * b1], q1 = rec4[2 * b1 + 1];
-				const float dx0 = p0.x - pfx, dy0 = p0.y - pfy, dx1 = p1.x - pfx, dy1 = p1.y - pfy;
-				const float power0 = -0.5f * (p0.z * dx0 * dx0 + q0.x * dy0 * dy0) - p0.w * dx0 * dy0;
-				const float power1 = -0.5f * (p1.z * dx1 * dx1 + q1.x * dy1 * dy1) - p1.w * dx1 * dy1;
-				const float a0 = q0.y * expf(power0);
-				const float a1 = q1.y * expf(power1);
-#if MGS_FWD_PREDICATED
-				blend_one(true, b0, power0, a0, rows + i * NQ);
-				blend_one(two, b1, power1, a1, rows + (i + 1) * NQ);
-#else
-				blend_one(b0, power0, a0, rows + i * NQ);
-				if (two) blend_one(b1, power1, a1, rows + (i + 1) * NQ);
-#endif
-				i += two ? 2 : 1;
+				for (int i = 0; i < 8 * NFT; i++) row[i] = (i < F) ? __ldg(f + i) : 0.f;
 			}
 		}
-		if (__all_sync(0xffffffffu, done)) {
-			// drain whatever is still in flight before the CTA exits
-			if (VEC) cp_async_wait<0>();
-			for (int k = waited; k < issued; k++) ring.wait(k);
-			break;
+		// ---- walk: one k-step (8 survivors) per trip, two survivors per step (the second one's expf overlaps the
+		// first one's recurrence); slots beyond cnt hold stale records and get zero weights ----
+		const int nks = (cnt + 7) >> 3;
+		int ks = 0;
+		for (; ks < nks; ks++) {
+			if (ks > 0 && __all_sync(0xffffffffu, done)) break;
+			const float4* q4 = s_q + 16 * ks;
+			float* wrow = s_w + 256 * ks;
+#pragma unroll
+			for (int u = 0; u < 8; u += 2) {
+				const float4 p0 = q4[2 * u], q0 = q4[2 * u + 1], p1 = q4[2 * u + 2], q1 = q4[2 * u + 3];
+				const float w0 = blend_step(8 * ks + u < cnt, p0, q0);
+				const float w1 = blend_step(8 * ks + u + 1 < cnt, p1, q1);
+				wrow[u * 32 + ((u & 3) == 0 ? lsw0 : lsw2)] = w0;
+				wrow[(u + 1) * 32 + (((u + 1) & 3) == 1 ? lsw1 : lsw3)] = w1;
+			}
 		}
-		// the batch whose last chunk was just blended frees its buffer for the batch RING ahead
-		if ((g & 1) && issued < nb) { ring.issue(issued); issued++; }
-		mask_cur = mask_next;
-	}
+		const int nk = ks;  // k-steps to contract
+		if (VEC) cp_async_wait<0>();
+		__syncwarp();
+		// ---- contract on the tensor cores ----
+		for (int ks = 0; ks < nk; ks++) {
+			const int g0 = 8 * ks + tig, g1 = g0 + 4;
+			// pixels 4 gid .. 4 gid + 3 of survivor g: one 16-byte group of the swizzled tile
+			const float4 wa = *reinterpret_cast<const float4*>(s_w + g0 * 32 + ((4 * gid) ^ (8 * (g0 & 3))));
+			const float4 wb = *reinterpret_cast<const float4*>(s_w + g1 * 32 + ((4 * gid) ^ (8 * (g1 & 3))));
+			uint32_t ahi[2][4], alo[2][4];
+			tf32_split(wa.x, ahi[0][0], alo[0][0]); tf32_split(wa.y, ahi[0][1], alo[0][1]);
+			tf32_split(wb.x, ahi[0][2], alo[0][2]); tf32_split(wb.y, ahi[0][3], alo[0][3]);
+			tf32_split(wa.z, ahi[1][0], alo[1][0]); tf32_split(wa.w, ahi[1][1], alo[1][1]);
+			tf32_split(wb.z, ahi[1][2], alo[1][2]); tf32_split(wb.w, ahi[1][3], alo[1][3]);
+			const float* row0 = s_rows + g0 * RS;
+			const float* row1 = s_rows + g1 * RS;
+			if (NFT > 0) {
+				float f0[4], f1[4];
+				load_feat<NFT>(row0, gid, f0);
+				load_feat<NFT>(row1, gid, f1);
+#pragma unroll
+				for (int nt = 0; nt < NFT; nt++) {
+					uint32_t bh0, bl0, bh1, bl1;
+					tf32_split(f0[nt], bh0, bl0);
+					tf32_split(f1[nt], bh1, bl1);
+					mma_3xtf32(acc[0][nt], ahi[0], alo[0], bh0, bh1, bl0, bl1);
+					mma_3xtf32(acc[1][nt], ahi[1], alo[1], bh0, bh1, bl0, bl1);
+				}
+			}
+			{
+				const float c0 = gid < 4 ? row0[L::RGBD + gid] : 0.f;
+				const float c1 = gid < 4 ? row1[L::RGBD + gid] : 0.f;
+				uint32_t bh0, bl0, bh1, bl1;
+				tf32_split(c0, bh0, bl0);
+				tf32_split(c1, bh1, bl1);
+				mma_3xtf32(acc[0][NFT], ahi[0], alo[0], bh0, bh1, bl0, bl1);
+				mma_3xtf32(acc[1][NFT], ahi[1], alo[1], bh0, bh1, bl0, bl1);
+			}
+		}
+		// the (< 32) survivors behind the chunk move to the head of the queue
+		const int left = qcount - cnt;
+		float4 m0, m1;
+		if (lane < left) { m0 = s_q[2 * (cnt + lane)]; m1 = s_q[2 * (cnt + lane) + 1]; }
+		__syncwarp();  // also: s_w and s_rows are rewritten by the next chunk
+		if (lane < left) { s_q[2 * lane] = m0; s_q[2 * lane + 1] = m1; }
+		qcount = left;
+		__syncwarp();
+		return __all_sync(0xffffffffu, done);
+	};
 
+	bool finished = false;
+	for (int k = 0; k < nb && !finished; k++) {
+		const float4* rec4 = ring.wait(k);
+		waited = k + 1;
+		const int lo = ring.batch_lo(k), n = ring.batch_n(k);
+		for (int c = 0; c < n && !finished; c += 32) {
+			const int j = c + lane;
+			float4 r0, r1;
+			bool hit = false;
+			if (j < n) {
+				r0 = rec4[2 * j]; r1 = rec4[2 * j + 1];
+				hit = rec_hits_block(r0, r1, fbx0, fbx1, fby0, fby1);
+			}
+			const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+			if (hit) {
+				const int e = qcount + __popc(mask & ((1u << lane) - 1u));
+				r1.z = __uint_as_float((uint32_t)(lo + j) + 1u);  // the cull extent is spent: keep the 1-based list position instead
+				s_q[2 * e] = r0;
+				s_q[2 * e + 1] = r1;
+			}
+			qcount += __popc(mask);
+			__syncwarp();
+			while (qcount >= FWD_CH && !finished) finished = process_chunk(FWD_CH);
+		}
+		// every survivor of this batch sits in the queue: its buffer is free for the batch RING ahead
+		if (!finished && issued < nb) { ring.issue(issued); issued++; }
+	}
+	if (!finished && qcount > 0) process_chunk(qcount);
+	for (int k = waited; k < issued; k++) ring.wait(k);  // no bulk copy may be in flight when the CTA exits
+
+	// ---- outputs ----
+	const size_t HW = (size_t)a.H * a.W;
 	if (inside) {
-		const size_t HW = (size_t)a.H * a.W;
 		const size_t pix = (size_t)a.W * pyi + pxi;
 		a.final_T[pix] = T;
 		a.n_contrib[pix] = last_contributor;
+	}
+	s_w[lane] = T;
+	__syncwarp();
+	const int ox = bx0 + gid;  // fragment role: this thread holds pixels (x = gid, y = 0..3)
+	if (ox < a.W) {
 #pragma unroll
-		for (int ch = 0; ch < 3; ch++) a.out_color[ch * HW + pix] = acc[ch] + T * a.bg[ch];
-		if (a.out_depth) a.out_depth[pix] = acc[3];
-		if (NQ > 1) {
+		for (int mt = 0; mt < 2; mt++) {
 #pragma unroll
-			for (int i = 0; i < 4 * (NQ - 1); i++)
-				if (i < F) a.out_feature[(size_t)i * HW + pix] = acc[4 + i];
+			for (int h = 0; h < 2; h++) {
+				const int y = 2 * mt + h, oy = by0 + y;
+				if (oy >= a.H) continue;
+				const size_t pix = (size_t)a.W * oy + ox;
+				const float Tp = s_w[4 * gid + y];
+#pragma unroll
+				for (int nt = 0; nt < NFT; nt++) {
+#pragma unroll
+					for (int e = 0; e < 2; e++) {
+						const int f = NFT * (2 * tig + e) + nt;
+						if (f < F) a.out_feature[(size_t)f * HW + pix] = acc[mt][nt][2 * h + e];
+					}
+				}
+#pragma unroll
+				for (int e = 0; e < 2; e++) {
+					const int c = 2 * tig + e;  // column of the {r,g,b,depth} tile
+					const float v = acc[mt][NFT][2 * h + e];
+					if (c < 3) a.out_color[(size_t)c * HW + pix] = v + Tp * a.bg[c];
+					else if (c == 3 && a.out_depth) a.out_depth[pix] = v;
+				}
+			}
 		}
 	}
 }
 
 int blend_supported(int F) { return F >= 0 && F <= 32; }
 
-int nq_for(int F)
-{
-	const int need = (4 + F + 3) / 4;
-	if (need <= 1) return 1;
-	if (need <= 2) return 2;
-	if (need <= 3) return 3;
-	if (need <= 5) return 5;
-	return 9;
-}
-
-// 128-bit / bulk feature copies need 16-byte aligned rows of a 16-byte multiple
+// 128-bit feature copies need 16-byte aligned rows of a 16-byte multiple
 bool feature_rows_vectorizable(const float* feature, int F)
 {
 	return F > 0 && (F & 3) == 0 && (reinterpret_cast<uintptr_t>(feature) & 15) == 0;
 }
 
-template <int NQ>
+template <int NFT>
 static void launch_fwd_t(const BlendArgs& a, cudaStream_t s)
 {
 	const int grid = a.grid_x * a.grid_y * 8;
-	// a feature row shorter than its padded NQ-1 quads would leave stale shared memory in the tail quads: only the
-	// exact fits take the bulk-copy path
-	const bool vec = (NQ == 1) || (feature_rows_vectorizable(a.feature, a.F) && a.F == 4 * (NQ - 1));
-	if (vec) blend_fwd_kernel<NQ, true><<<grid, 32, 0, s>>>(a);
-	else blend_fwd_kernel<NQ, false><<<grid, 32, 0, s>>>(a);
+	// the cp.async row gather copies whole 8-wide feature tiles: exact fits only; other widths take the padded path
+	const bool vec = (NFT == 0) || (a.F == 8 * NFT && feature_rows_vectorizable(a.feature, a.F));
+	if (vec) blend_fwd_kernel<NFT, true><<<grid, 32, 0, s>>>(a);
+	else blend_fwd_kernel<NFT, false><<<grid, 32, 0, s>>>(a);
 }
+
+void launch_blend_fwd_simt(const BlendArgs& a, cudaStream_t s);
 
 void launch_blend_fwd(const BlendArgs& a, cudaStream_t s)
 {
-	switch (a.nq) {
+	if (blend_variant() & 1) { launch_blend_fwd_simt(a, s); return; }
+	switch (nft_for(a.F)) {
+	case 0: launch_fwd_t<0>(a, s); break;
 	case 1: launch_fwd_t<1>(a, s); break;
 	case 2: launch_fwd_t<2>(a, s); break;
-	case 3: launch_fwd_t<3>(a, s); break;
-	case 5: launch_fwd_t<5>(a, s); break;
-	default: launch_fwd_t<9>(a, s); break;
+	default: launch_fwd_t<4>(a, s); break;
 	}
 }
 

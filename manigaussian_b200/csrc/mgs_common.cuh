@@ -4,7 +4,7 @@
 // auxiliary.h, rasterizer_impl.cu of the reference).  Nothing here is copied from the reference;
 // the per-Gaussian arithmetic is written so that nvcc's FMA contraction sees the same expression
 // shapes as in the reference (left-to-right sums of products), which is what makes tile ids and
-// sort keys bit-exact (checked on the GPU against oracle/_ref by tests/test_parity_reference.py).
+// sort keys bit-exact (checked on the GPU against oracle/_ref by tests/test_parity_gpu.py::test_vs_compiled_reference and tests/test_baseline_sizes_gpu.py).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -142,6 +142,7 @@ void launch_ranges_and_pack(int R, int num_tiles, const uint32_t* tile_keys, con
 
 // blend_fwd.cu / blend_bwd.cu
 int blend_supported(int F);
+int blend_variant();  // bit 0 / bit 1: use the round-1 SIMT forward / backward blend (MGS_BLEND=simt|simt_fwd|simt_bwd; A/B measurements only)
 int nq_for(int F);
 void launch_blend_fwd(const BlendArgs& a, cudaStream_t s);
 void launch_blend_bwd(const BlendArgs& a, cudaStream_t s);

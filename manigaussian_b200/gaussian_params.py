@@ -56,11 +56,12 @@ def activate_gaussians_raw(means, rot, scales, opac, feature, d_means, d_rot, d_
     F = 0 if feature is None else int(feature.shape[1])
     o_means, o_rot, o_scales, o_opac = (torch.empty_like(t) for t in (means, rot, scales, opac))
     o_feat = torch.empty_like(feature) if F > 0 else None
-    _b.check(_b.lib().mgs_activate(P, F, _ptr(means), _ptr(d_means), _ptr(rot), _ptr(d_rot), _ptr(scales), _ptr(d_scales),
-                                   _ptr(opac), _ptr(feature), scale_mode, float(scale_max), opacity_mode,
-                                   int(bool(rot_normalize)), int(bool(feature_normalize)),
-                                   _ptr(o_means), _ptr(o_rot), _ptr(o_scales), _ptr(o_opac), _ptr(o_feat), _stream(dev)),
-              "mgs_activate")
+    with torch.cuda.device(dev):  # the tensors' device need not be the current one (train_device=rank without set_device)
+        _b.check(_b.lib().mgs_activate(P, F, _ptr(means), _ptr(d_means), _ptr(rot), _ptr(d_rot), _ptr(scales), _ptr(d_scales),
+                                       _ptr(opac), _ptr(feature), scale_mode, float(scale_max), opacity_mode,
+                                       int(bool(rot_normalize)), int(bool(feature_normalize)),
+                                       _ptr(o_means), _ptr(o_rot), _ptr(o_scales), _ptr(o_opac), _ptr(o_feat), _stream(dev)),
+                  "mgs_activate")
     return o_means, o_rot, o_scales, o_opac, o_feat
 
 
@@ -76,12 +77,13 @@ def activate_gaussians_backward_raw(means, rot, scales, opac, feature, d_means, 
     like = (means, means, rot, rot, scales, scales, opac, feature)
     have = (g_means, g_means, g_rot, g_rot, g_scales, g_scales, g_opac, g_feature)
     outs = [torch.empty_like(l) if (w and h is not None and l is not None) else None for w, l, h in zip(want, like, have)]
-    _b.check(_b.lib().mgs_activate_backward(P, F, _ptr(means), _ptr(d_means), _ptr(rot), _ptr(d_rot), _ptr(scales),
-                                            _ptr(d_scales), _ptr(opac), _ptr(feature), scale_mode, float(scale_max),
-                                            opacity_mode, int(bool(rot_normalize)), int(bool(feature_normalize)),
-                                            _ptr(g_means), _ptr(g_rot), _ptr(g_scales), _ptr(g_opac), _ptr(g_feature),
-                                            *[_ptr(o) for o in outs], _stream(dev)),
-              "mgs_activate_backward")
+    with torch.cuda.device(dev):
+        _b.check(_b.lib().mgs_activate_backward(P, F, _ptr(means), _ptr(d_means), _ptr(rot), _ptr(d_rot), _ptr(scales),
+                                                _ptr(d_scales), _ptr(opac), _ptr(feature), scale_mode, float(scale_max),
+                                                opacity_mode, int(bool(rot_normalize)), int(bool(feature_normalize)),
+                                                _ptr(g_means), _ptr(g_rot), _ptr(g_scales), _ptr(g_opac), _ptr(g_feature),
+                                                *[_ptr(o) for o in outs], _stream(dev)),
+                  "mgs_activate_backward")
     return outs
 
 
@@ -92,8 +94,9 @@ def normalize_features_raw(feature):
     P, F = feature.shape
     out = torch.empty_like(feature)
     if P and F:
-        _b.check(_b.lib().mgs_activate(P, F, None, None, None, None, None, None, None, _ptr(feature), 0, 0.0, 0, 0, 1,
-                                       None, None, None, None, _ptr(out), _stream(feature.device)), "mgs_activate")
+        with torch.cuda.device(feature.device):
+            _b.check(_b.lib().mgs_activate(P, F, None, None, None, None, None, None, None, _ptr(feature), 0, 0.0, 0, 0, 1,
+                                           None, None, None, None, _ptr(out), _stream(feature.device)), "mgs_activate")
     return out
 
 
@@ -102,9 +105,10 @@ def normalize_features_backward_raw(feature, g):
     g = _prep(g, feature.device)
     out = torch.empty_like(feature)
     if P and F:
-        _b.check(_b.lib().mgs_activate_backward(P, F, None, None, None, None, None, None, None, _ptr(feature), 0, 0.0, 0, 0, 1,
-                                                None, None, None, None, _ptr(g), None, None, None, None, None, None, None,
-                                                _ptr(out), _stream(feature.device)), "mgs_activate_backward")
+        with torch.cuda.device(feature.device):
+            _b.check(_b.lib().mgs_activate_backward(P, F, None, None, None, None, None, None, None, _ptr(feature), 0, 0.0, 0, 0, 1,
+                                                    None, None, None, None, _ptr(g), None, None, None, None, None, None, None,
+                                                    _ptr(out), _stream(feature.device)), "mgs_activate_backward")
     return out
 
 

@@ -11,7 +11,7 @@
  * so this restatement is pinned against outputs of the reference itself: the unmodified
  * DGR sources compiled into oracle/_ref (oracle/build_ref.py) are run on a B200 by
  * tests/golden/make_golden.py and the resulting small fixtures are committed under
- * tests/golden/.  tests/test_oracle_golden.py checks this file against them.
+ * tests/golden/.  tests/test_oracle_cpu.py::test_oracle_against_reference_golden checks this file against them.
  *
  * Every function cites the reference file:line it follows.  Channel count for the
  * "language feature" planes is a run-time value F here (compile-time

@@ -92,7 +92,7 @@ def parse_ref_image(buf, N):
 
 # --------------------------------------------------------------------------- inputs
 def make_inputs(P, W, H, F=0, seed=0, view=0, num_views=4, sh_degree=1, precomp_colors=False, precomp_cov=False,
-                scale0=None, bg=(0.0, 0.0, 0.0)):
+                scale0=None, bg=(0.0, 0.0, 0.0), depth=False):
     cam = scenes.make_camera(W, H, view, num_views)
     g = scenes.make_gaussians(P, F=F, sh_degree=sh_degree, seed=seed, scale0=scale0, precomp_colors=precomp_colors)
     g["cov3D_precomp"] = None
@@ -107,7 +107,7 @@ def make_inputs(P, W, H, F=0, seed=0, view=0, num_views=4, sh_degree=1, precomp_
         g["cov3D_precomp"] = np.stack([Sig[:, 0, 0], Sig[:, 0, 1], Sig[:, 0, 2], Sig[:, 1, 1], Sig[:, 1, 2], Sig[:, 2, 2]],
                                       -1).astype(np.float32)
         g["scales"], g["rotations"] = None, None
-    ct = scenes.make_cotangents(W, H, F, seed=seed)
+    ct = scenes.make_cotangents(W, H, F, seed=seed, depth=depth)
     return dict(cam=cam, g=g, ct=ct, bg=np.asarray(bg, np.float32), P=P, W=W, H=H, F=F)
 
 
@@ -132,7 +132,8 @@ def run_oracle(inp, backward=True):
 
 
 # --------------------------------------------------------------------------- product path (CUDA)
-def run_ours(inp, backward=True, debug=False):
+def run_ours(inp, backward=True, debug=False, scale_modifier=1.0, prefiltered=False, depth=False):
+    """depth=True renders the view-space depth plane too (fw['out_depth']) and feeds inp['ct']['dL_ddepth'] to the backward."""
     import torch
     from manigaussian_b200 import rasterizer as R
     cam, g, ct = inp["cam"], inp["g"], inp["ct"]
@@ -140,9 +141,10 @@ def run_ours(inp, backward=True, debug=False):
     include = F > 0
     feat = _t(g["feature"]) if include else torch.zeros((P, 3), device="cuda")
     args = (_t(inp["bg"]), _t(g["means3D"]), _t(g["colors_precomp"]), feat, _t(g["opacities"]), _t(g["scales"]),
-            _t(g["rotations"]), 1.0, _t(g["cov3D_precomp"]), _t(cam["viewmatrix"]), _t(cam["projmatrix"]),
-            cam["tanfovx"], cam["tanfovy"], H, W, _t(g["shs"]), g["sh_degree"], _t(cam["campos"]), False, debug, include)
-    num_rendered, color, feature, radii, geomB, binB, imgB = R.rasterize_gaussians_raw(*args)
+            _t(g["rotations"]), scale_modifier, _t(g["cov3D_precomp"]), _t(cam["viewmatrix"]), _t(cam["projmatrix"]),
+            cam["tanfovx"], cam["tanfovy"], H, W, _t(g["shs"]), g["sh_degree"], _t(cam["campos"]), prefiltered, debug, include)
+    out = R.rasterize_gaussians_raw(*args, return_depth=depth)
+    num_rendered, color, feature, radii, geomB, binB, imgB = out[:7]
     torch.cuda.synchronize()
     N, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
 
@@ -154,6 +156,8 @@ def run_ours(inp, backward=True, debug=False):
 
     fw = dict(P=P, W=W, H=H, F=F, M=0 if g["shs"] is None else g["shs"].shape[1], num_rendered=num_rendered,
               out_color=color.cpu().numpy(), out_feature=feature.cpu().numpy(), radii=radii.cpu().numpy())
+    if depth:
+        fw["out_depth"] = out[7].cpu().numpy()
     for name, dt, cnt in (("depths", torch.float32, P), ("means2D", torch.float32, 2 * P), ("cov3D", torch.float32, 6 * P),
                           ("conic_opacity", torch.float32, 4 * P), ("rgbd", torch.float32, 4 * P),
                           ("tiles_touched", torch.int32, P), ("point_offsets", torch.int32, P), ("clamped", torch.uint8, P),
@@ -181,9 +185,10 @@ def run_ours(inp, backward=True, debug=False):
     bw = None
     if backward:
         grads = R.rasterize_gaussians_backward_raw(
-            args[0], args[1], radii, args[2], feat, args[5], args[6], 1.0, args[8], args[9], args[10], cam["tanfovx"],
+            args[0], args[1], radii, args[2], feat, args[5], args[6], scale_modifier, args[8], args[9], args[10], cam["tanfovx"],
             cam["tanfovy"], _t(ct["dL_dcolor"]), _t(ct["dL_dfeature"]) if include else torch.zeros((1,), device="cuda"),
-            args[15], g["sh_degree"], args[17], geomB, num_rendered, binB, imgB, debug, include)
+            args[15], g["sh_degree"], args[17], geomB, num_rendered, binB, imgB, debug, include,
+            dL_dout_depth=_t(ct["dL_ddepth"]) if depth else None)
         torch.cuda.synchronize()
         names = ("dL_dmeans2D", "dL_dcolors", "dL_dfeature", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
                  "dL_dscales", "dL_drotations")
@@ -192,28 +197,37 @@ def run_ours(inp, backward=True, debug=False):
 
 
 # --------------------------------------------------------------------------- compiled reference (CUDA)
-def run_reference(inp, backward=True):
-    """Runs oracle/_ref (the reference's own kernels).  Features are padded/truncated to the build's width."""
+def run_reference(inp, backward=True, scale_modifier=1.0, prefiltered=False, depth=False):
+    """Runs oracle/_ref (the reference's own kernels).  Features are padded/truncated to the build's width.  The reference
+    renders no depth: with depth=True view-space z rides in the spare feature channel F of the build (SURVEY.md finding 4),
+    fw['out_depth'] is that channel's image and dL/dz is chained into dL_dmeans3D by hand (z = V[2,:3] . p + V[2,3])."""
     import torch
     P, W, H, F = inp["P"], inp["W"], inp["H"], inp["F"]
-    Fb = 32 if F > 3 else 3
+    Fb = 32 if F + (1 if depth else 0) > 3 else 3
+    assert F + (1 if depth else 0) <= Fb
     mod = load_reference(Fb)
     if mod is None:
         return None, None
     cam, g, ct = inp["cam"], inp["g"], inp["ct"]
-    include = F > 0
+    include = F > 0 or depth
     feat = torch.zeros((P, Fb), device="cuda")
-    if include:
+    if F > 0:
         feat[:, :F] = _t(g["feature"])
+    vm = cam["viewmatrix"].reshape(-1)
+    zrow = np.array([vm[2], vm[6], vm[10]], np.float32)
+    if depth:
+        feat[:, F] = _t(g["means3D"]) @ _t(zrow) + float(vm[14])
     args = (_t(inp["bg"]), _t(g["means3D"]), _t(g["colors_precomp"]), feat, _t(g["opacities"]), _t(g["scales"]),
-            _t(g["rotations"]), 1.0, _t(g["cov3D_precomp"]), _t(cam["viewmatrix"]), _t(cam["projmatrix"]),
-            cam["tanfovx"], cam["tanfovy"], H, W, _t(g["shs"]), g["sh_degree"], _t(cam["campos"]), False, False, include)
+            _t(g["rotations"]), scale_modifier, _t(g["cov3D_precomp"]), _t(cam["viewmatrix"]), _t(cam["projmatrix"]),
+            cam["tanfovx"], cam["tanfovy"], H, W, _t(g["shs"]), g["sh_degree"], _t(cam["campos"]), prefiltered, False, include)
     num_rendered, color, feature, radii, geomB, binB, imgB = mod.rasterize_gaussians(*args)
     torch.cuda.synchronize()
     N, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
     gs, bs, ims = parse_ref_geom(geomB, P), parse_ref_binning(binB, num_rendered), parse_ref_image(imgB, N)
     fw = dict(P=P, W=W, H=H, F=F, num_rendered=num_rendered, out_color=color.cpu().numpy(), radii=radii.cpu().numpy(),
               out_feature=feature[:F].cpu().numpy() if include else feature.cpu().numpy())
+    if depth:
+        fw["out_depth"] = feature[F].cpu().numpy()
     fw["depths"] = gs["depths"].cpu().numpy()
     fw["means2D"] = gs["means2D"].cpu().numpy().reshape(P, 2)
     fw["cov3D"] = gs["cov3D"].cpu().numpy().reshape(P, 6)
@@ -229,16 +243,20 @@ def run_reference(inp, backward=True):
     bw = None
     if backward:
         dF = torch.zeros((Fb, H, W), device="cuda")
-        if include:
+        if F > 0:
             dF[:F] = _t(ct["dL_dfeature"])
+        if depth:
+            dF[F] = _t(ct["dL_ddepth"])
         grads = mod.rasterize_gaussians_backward(
-            args[0], args[1], radii, args[2], feat, args[5], args[6], 1.0, args[8], args[9], args[10], cam["tanfovx"],
+            args[0], args[1], radii, args[2], feat, args[5], args[6], scale_modifier, args[8], args[9], args[10], cam["tanfovx"],
             cam["tanfovy"], _t(ct["dL_dcolor"]), dF if include else torch.zeros((1,), device="cuda"), args[15],
             g["sh_degree"], args[17], geomB, num_rendered, binB, imgB, False, include)
         torch.cuda.synchronize()
         names = ("dL_dmeans2D", "dL_dcolors", "dL_dfeature", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
                  "dL_dscales", "dL_drotations")
         bw = {n: t.cpu().numpy() for n, t in zip(names, grads)}
+        if depth:
+            bw["dL_dmeans3D"] = bw["dL_dmeans3D"] + bw["dL_dfeature"][:, F:F + 1] * zrow[None, :]
         if include:
             bw["dL_dfeature"] = bw["dL_dfeature"][:, :F]
     return fw, bw
