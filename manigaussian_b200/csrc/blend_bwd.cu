@@ -26,11 +26,19 @@
 //   6. flush     per (block, Gaussian): 3 red.global.add.v4.f32 of the 10 small gradients + the feature row as
 //                red.v4 straight from the D fragments (column gid of feature tile nt is feature NFT*gid + nt, so a thread
 //                holds 8 consecutive features of its four Gaussians).
-// Index assignment (pixels, Gaussians, channels <-> MMA rows, columns, k) makes the fragment traffic wide: with pixel
-// p = 8 ks + 2 tig + e as k-slot (ks, tig + 4 e) and the [g][pixel] tiles stored in the column order
-// pi(p) = 8 tig + 2 ks + e, a thread's A values of GEMM 2/3 are two LDS.128 per Gaussian row and GEMM 1's D fragments
-// store as 8-byte pairs; channel rows use stride 36 floats, which makes GEMM 1's row loads and GEMM 2's cotangent loads
-// conflict free without padding the gather.
+// Index assignment.  An MMA A operand is four consecutive registers, a B operand two; a register move per operand would
+// cost more than the tensor cores save, so every shared-memory tile is laid out such that operands ARRIVE in place:
+//   pixels      p = 2 pi + e  (pair pi = 0..15).  K-side (GEMM 2/3): k-step pi >> 2, slots tig = pi & 3 (e = 0) and
+//               tig + 4 (e = 1).  M-side (GEMM 1): tile pi >> 3, rows gid = pi & 7 (e = 0) and gid + 8 (e = 1).
+//   survivors   j.  M-side (GEMM 2/3): tile j >> 4, rows gid = (j & 15) >> 1 (even j) and gid + 8 (odd j).
+//               N-side (GEMM 1): tile j >> 3, column j & 7.
+//   channels    K-side (GEMM 1): step ch >> 3, slots tig = (ch & 7) >> 1 (even ch) and tig + 4 (odd ch).
+//               N-side (GEMM 2): column gid of feature tile nt is feature NFT gid + nt; {r,g,b,depth} tile: column gid.
+//   s_g  [pi][ch][e]              cotangents: GEMM 1's A quad {(e0,ch),(e1,ch),(e0,ch+1),(e1,ch+1)} is one LDS.128, GEMM 2's
+//                                 B pairs {(e0,ch),(e1,ch)} for a thread's NFT consecutive channels are LDS.128s
+//   s_rows [j][ch]                channel rows as gathered: GEMM 1's B pair {ch, ch+1} is one LDS.64
+//   s_x, s_wgt [pi][j >> 1][e][j & 1]   GEMM 1's D fragment is one STS.128, GEMM 2/3's A quad one LDS.128; the walk
+//                                 (lane = pixel) reads Wd and writes q in place
 #include "blend_common.cuh"
 #include "blend_mma.cuh"
 
@@ -43,7 +51,7 @@ namespace mgs {
 #define MGS_BWD_MIN_CTAS 12
 #endif
 #ifndef MGS_BWD_BATCH
-#define MGS_BWD_BATCH 32
+#define MGS_BWD_BATCH 64
 #endif
 constexpr int BWD_CH = MGS_BWD_CH;        // survivors per chunk: 16 or 32 (whole 16-row MMA tiles)
 constexpr int BWD_QCAP = BWD_CH + 32;
@@ -55,15 +63,18 @@ static_assert(BWD_BATCH % 32 == 0, "backward record batch");
 template <int NFT, bool VEC>
 __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendArgs a)
 {
-	constexpr int NT = NFT + 1;          // channel column tiles: NFT feature tiles + {r,g,b,depth}
-	constexpr int RS = 8 * NFT + 4;      // channel-row stride (floats): [8 NFT features | r g b depth]
+	constexpr int NT = NFT + 1;          // channel tiles of 8: NFT feature tiles + {r,g,b,depth, 4 x zero}
+	constexpr int CHP = 8 * NT;          // padded channel count
+	constexpr int RS = CHP;              // channel-row stride (floats): [8 NFT features | r g b depth | 0 0 0 0]
 	constexpr int RGBD = 8 * NFT;
-	constexpr int ROWS_FLOATS = BWD_CH * (RS > 32 ? RS : 32);  // the rows buffer is reused for the wgt tile
+	constexpr int GS = 2 * CHP;          // s_g stride per pixel pair
+	constexpr int XS = 2 * BWD_CH + 4;   // s_x / s_wgt stride per pixel pair (+4: spreads the pairs over the banks)
+	constexpr int ROWS_FLOATS = (BWD_CH * RS > 16 * XS) ? BWD_CH * RS : 16 * XS;  // the rows buffer is reused for the wgt tile
 	__shared__ __align__(128) InstRec s_rec[RING * BWD_BATCH];
 	__shared__ __align__(16) float4 s_q[BWD_QCAP * 2];     // survivor queue (linear, back to front): {x,y,ca,cb}, {cc,op,pos,id}
-	__shared__ __align__(16) float s_rows[ROWS_FLOATS];    // C[g][RS]; after GEMM 1: wgt[g][32]
-	__shared__ __align__(16) float s_x[BWD_CH * 32];       // Wd[g][32]; the walk overwrites it with q in place; then moments
-	__shared__ __align__(16) float s_g[32 * RS];           // Gpx[p][RS]: cotangent rows of the block's pixels
+	__shared__ __align__(16) float s_rows[ROWS_FLOATS];    // C[j][RS]; after GEMM 1: wgt tile
+	__shared__ __align__(16) float s_x[16 * XS];           // Wd tile; the walk overwrites it with q in place; then per-Gaussian staging
+	__shared__ __align__(16) float s_g[16 * GS];           // cotangent rows of the block's pixels
 	__shared__ __align__(8) uint64_t s_bar[RING];
 
 	const int lane = threadIdx.x;
@@ -92,12 +103,13 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 			if (a.dL_ddepth) g4[3] = a.dL_ddepth[pix];
 		}
 		bgterm = T * (a.bg[0] * g4[0] + a.bg[1] * g4[1] + a.bg[2] * g4[2]);
-		float* grow = s_g + lane * RS;
-		*reinterpret_cast<float4*>(grow + RGBD) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+		float* grow = s_g + (lane >> 1) * GS + (lane & 1);  // element (pixel, ch) at [pi][ch][e]
+#pragma unroll
+		for (int c = 0; c < 4; c++) { grow[2 * (RGBD + c)] = g4[c]; grow[2 * (RGBD + 4 + c)] = 0.f; }
 		if (NFT > 0) {
 #pragma unroll
 			for (int i = 0; i < 8 * NFT; i++)
-				grow[i] = (inside && i < F && a.dL_dfeature) ? a.dL_dfeature[(size_t)i * HW + pix] : 0.f;
+				grow[2 * i] = (inside && i < F && a.dL_dfeature) ? a.dL_dfeature[(size_t)i * HW + pix] : 0.f;
 		}
 	}
 	uint32_t maxc = nc;
@@ -117,9 +129,7 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 
 	const float pfx = (float)pxi, pfy = (float)pyi;
 	float S = 0.f;  // sum over the contributors behind the current one of a_j T_j (c_j . g)
-	// column of pixel `lane` in the [g][pixel] tiles: pi(p) = 8 ((p >> 1) & 3) + 2 (p >> 3) + (p & 1); rows g with g & 1 set
-	// have their 16-byte groups swapped pairwise (conflict-free 128-bit reads of two adjacent rows)
-	const int pcol0 = 8 * ((lane >> 1) & 3) + 2 * (lane >> 3) + (lane & 1), pcol1 = pcol0 ^ 4;
+	const int xofs = (lane >> 1) * XS + (lane & 1) * 2;  // this pixel's slot in the [pi][j >> 1][e][j & 1] tiles
 	// GEMM 3's B operand: moments basis of the two pixels of k-slots (ks, tig) and (ks, tig + 4): p = 8 ks + 2 tig + e,
 	// x = p >> 2, y = p & 3; column gid selects {1, x, y, x^2, x y, y^2, 0, 0}
 	uint32_t ymom[4][2];
@@ -140,14 +150,20 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 	auto process_chunk = [&](int cnt) {
 		// ---- 1. gather the channel rows ----
 		if (VEC) {
-			constexpr int NPR = 2 * NFT + 1;
-			const int npieces = cnt * NPR;
-			for (int idx = lane; idx < npieces; idx += 32) {
-				const int r = idx / NPR, q = idx - r * NPR;
-				const uint32_t id = __float_as_uint(s_q[2 * r + 1].w);
-				const float4* src = (q == 2 * NFT) ? (a.rgbd + id) : (reinterpret_cast<const float4*>(a.feature + (size_t)id * F) + q);
-				cp_async16(s_rows + r * RS + 4 * q, src);
+			// lane r knows the Gaussian id of survivor r; 32 / (2 NFT) feature rows are copied per trip (lane = row x 16-byte
+			// piece), the id travelling by shuffle
+			const uint32_t myid = lane < cnt ? __float_as_uint(s_q[2 * lane + 1].w) : 0u;
+			if (NFT > 0) {
+				constexpr int NPF = NFT > 0 ? 2 * NFT : 1, RPI = 32 / NPF;
+				const int sub = lane / NPF, q = lane % NPF;
+#pragma unroll
+				for (int it = 0; it < BWD_CH / RPI; it++) {
+					const int r = it * RPI + sub;
+					const uint32_t id = __shfl_sync(0xffffffffu, myid, r);
+					if (r < cnt) cp_async16(s_rows + r * RS + 4 * q, reinterpret_cast<const float4*>(a.feature + (size_t)id * (8 * NFT)) + q);
+				}
 			}
+			if (lane < cnt) cp_async16(s_rows + lane * RS + RGBD, a.rgbd + myid);
 			cp_async_commit();
 			cp_async_wait<0>();
 		} else if (lane < cnt) {
@@ -161,89 +177,81 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 			}
 		}
 		__syncwarp();
-		// ---- 2. GEMM 1: Wd[g][p] = C[g][:] . Gpx[p][:]   (M = g, N = p (4 tiles), K = channels) ----
+		// ---- 2. GEMM 1: Wd[p][j] = Gpx[p][:] . C[j][:]   (M = pixels (2 tiles), N = survivors, K = channels) ----
 		{
-			float wd[BWD_MT][4][4];
+			float wd[2][BWD_CH / 8][4];
 #pragma unroll
-			for (int mt = 0; mt < BWD_MT; mt++)
+			for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-				for (int nt = 0; nt < 4; nt++)
+				for (int nt = 0; nt < BWD_CH / 8; nt++)
 #pragma unroll
 					for (int i = 0; i < 4; i++) wd[mt][nt][i] = 0.f;
-			// k-slot (ks, tig + 4 e) of feature step ks is feature 2 NFT tig + 2 ks + e: a thread reads 2 NFT consecutive floats
-			// of each of its rows; the last step is {r,g,b,depth}[tig] with the upper half of the slots empty
 #pragma unroll
 			for (int ks = 0; ks < NT; ks++) {
-				uint32_t ahi[BWD_MT][4], alo[BWD_MT][4], bhi[4][2], blo[4][2];
+				uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
-				for (int mt = 0; mt < BWD_MT; mt++) {
-#pragma unroll
-					for (int h = 0; h < 2; h++) {
-						const float* row = s_rows + (16 * mt + 8 * h + gid) * RS;
-						float v0, v1;
-						if (ks < NFT) { const float2 v = *reinterpret_cast<const float2*>(row + 2 * NFT * tig + 2 * ks); v0 = v.x; v1 = v.y; }
-						else { v0 = row[RGBD + tig]; v1 = 0.f; }
-						tf32_split(v0, ahi[mt][h], alo[mt][h]);
-						tf32_split(v1, ahi[mt][2 + h], alo[mt][2 + h]);
-					}
+				for (int mt = 0; mt < 2; mt++) {
+					const float4 v = *reinterpret_cast<const float4*>(s_g + (8 * mt + gid) * GS + (8 * ks + 2 * tig) * 2);
+					tf32_split(v.x, ahi[mt][0], alo[mt][0]); tf32_split(v.y, ahi[mt][1], alo[mt][1]);
+					tf32_split(v.z, ahi[mt][2], alo[mt][2]); tf32_split(v.w, ahi[mt][3], alo[mt][3]);
 				}
 #pragma unroll
-				for (int nt = 0; nt < 4; nt++) {
-					const float* row = s_g + (8 * nt + gid) * RS;
-					float v0, v1;
-					if (ks < NFT) { const float2 v = *reinterpret_cast<const float2*>(row + 2 * NFT * tig + 2 * ks); v0 = v.x; v1 = v.y; }
-					else { v0 = row[RGBD + tig]; v1 = 0.f; }
-					tf32_split(v0, bhi[nt][0], blo[nt][0]);
-					tf32_split(v1, bhi[nt][1], blo[nt][1]);
-				}
-#pragma unroll
-				for (int mt = 0; mt < BWD_MT; mt++)
-#pragma unroll
-					for (int nt = 0; nt < 4; nt++) mma_3xtf32(wd[mt][nt], ahi[mt], alo[mt], bhi[nt][0], bhi[nt][1], blo[nt][0], blo[nt][1]);
-			}
-			// D fragment (mt, nt): rows g = 16 mt + gid (+8), pixels p = 8 nt + 2 tig + e -> columns pi(p) = 8 tig + 2 nt + e
-#pragma unroll
-			for (int mt = 0; mt < BWD_MT; mt++) {
-#pragma unroll
-				for (int h = 0; h < 2; h++) {
-					const int g = 16 * mt + 8 * h + gid;
-					float* xrow = s_x + g * 32;
-					const int sw = 4 * (g & 1);
-#pragma unroll
-					for (int nt = 0; nt < 4; nt++)
-						*reinterpret_cast<float2*>(xrow + ((8 * tig + 2 * nt) ^ sw)) = make_float2(wd[mt][nt][2 * h], wd[mt][nt][2 * h + 1]);
+				for (int nt = 0; nt < BWD_CH / 8; nt++) {
+					const float2 v = *reinterpret_cast<const float2*>(s_rows + (8 * nt + gid) * RS + 8 * ks + 2 * tig);
+					uint32_t bh0, bl0, bh1, bl1;
+					tf32_split(v.x, bh0, bl0);
+					tf32_split(v.y, bh1, bl1);
+					mma_3xtf32(wd[0][nt], ahi[0], alo[0], bh0, bh1, bl0, bl1);
+					mma_3xtf32(wd[1][nt], ahi[1], alo[1], bh0, bh1, bl0, bl1);
 				}
 			}
+			// D fragment (mt, nt): pixels (pi = 8 mt + gid, e = 0 | 1), survivors 8 nt + 2 tig (+1): one 16-byte store
+#pragma unroll
+			for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+				for (int nt = 0; nt < BWD_CH / 8; nt++)
+					*reinterpret_cast<float4*>(s_x + (8 * mt + gid) * XS + (4 * nt + tig) * 4) =
+						make_float4(wd[mt][nt][0], wd[mt][nt][1], wd[mt][nt][2], wd[mt][nt][3]);
 		}
 		__syncwarp();  // Wd complete; the rows buffer is free for the wgt tile
-		// ---- 3. walk, back to front (queue order): lane = pixel ----
+		// ---- 3. walk, back to front (queue order): lane = pixel.  Per k-step of 8 survivors: first the eight footprint
+		// evaluations (independent, they overlap in the pipeline), then the short sequential recurrence on T and S. ----
 		float* s_wgt = s_rows;
-#pragma unroll 4
-		for (int j = 0; j < BWD_CH; j++) {
-			const float4 r0 = s_q[2 * j], r1 = s_q[2 * j + 1];
-			const int col = (j & 1) ? pcol1 : pcol0;
-			const float wdot = s_x[j * 32 + col];
-			const float dx = r0.x - pfx, dy = r0.y - pfy;
-			const float ca = r0.z, cb = r0.w, cc = r1.x, op = r1.y;
-			const float power = -0.5f * (ca * dx * dx + cc * dy * dy) - cb * dx * dy;
-			// ex2.approx-based exp (rel. error ~1e-6); the alpha >= 1/255 decision must agree with the forward's (which uses
-			// expf like the reference), so the rare borderline pairs are re-evaluated exactly
-			float G = __expf(power);
-			float alpha = min(ALPHA_MAX, op * G);
-			if (fabsf(alpha - ALPHA_MIN) < 2e-5f * ALPHA_MIN * 8.f) {
-				G = expf(power);
-				alpha = min(ALPHA_MAX, op * G);
+#pragma unroll 1
+		for (int j0 = 0; j0 < BWD_CH; j0 += 8) {
+			float al[8], opG[8], rinv[8];  // alpha, opacity * G, 1 / (1 - alpha); alpha = opG = 0, rinv = 1 for pairs that did not contribute
+#pragma unroll
+			for (int u = 0; u < 8; u++) {
+				const int j = j0 + u;
+				const float4 r0 = s_q[2 * j], r1 = s_q[2 * j + 1];
+				const float dx = r0.x - pfx, dy = r0.y - pfy;
+				const float op = r1.y;
+				const float power = -0.5f * (r0.z * dx * dx + r1.x * dy * dy) - r0.w * dx * dy;
+				// ex2.approx-based exp (rel. error ~1e-6); the alpha >= 1/255 decision must agree with the forward's (which uses
+				// expf like the reference), so the rare borderline pairs are re-evaluated exactly
+				float G = __expf(power);
+				float alpha = min(ALPHA_MAX, op * G);
+				if (fabsf(alpha - ALPHA_MIN) < 2e-5f * ALPHA_MIN * 8.f) {
+					G = expf(power);
+					alpha = min(ALPHA_MAX, op * G);
+				}
+				const bool valid = (j < cnt) && (__float_as_uint(r1.z) <= nc) && (power <= 0.0f) && (alpha >= ALPHA_MIN);
+				al[u] = valid ? alpha : 0.f;
+				opG[u] = valid ? op * G : 0.f;
+				rinv[u] = __fdividef(1.f, 1.f - al[u]);
 			}
-			const bool valid = (j < cnt) && (__float_as_uint(r1.z) <= nc) && (power <= 0.0f) && (alpha >= ALPHA_MIN);
-			const float rinv = __fdividef(1.f, 1.f - alpha);
-			const float Tk = T * rinv;                                 // transmittance in front of this Gaussian
-			const float wgt = alpha * Tk;                              // d(pixel channel) / d(colour of this Gaussian)
-			const float dL_dalpha = Tk * wdot - (S + bgterm) * rinv;
-			const float q = op * dL_dalpha * G;                        // dL/dG * G
-			s_wgt[j * 32 + col] = valid ? wgt : 0.f;
-			s_x[j * 32 + col] = valid ? q : 0.f;
-			T = valid ? Tk : T;
-			S = valid ? fmaf(wgt, wdot, S) : S;
+#pragma unroll
+			for (int u = 0; u < 8; u++) {
+				const int jofs = (j0 >> 1) * 4 + (u >> 1) * 4 + (u & 1);  // survivor j0 + u
+				const float wdot = s_x[xofs + jofs];
+				const float Tk = T * rinv[u];                                 // transmittance in front of this Gaussian
+				const float wgt = al[u] * Tk;                                 // d(pixel channel) / d(colour of this Gaussian)
+				const float dL_dalpha = Tk * wdot - (S + bgterm) * rinv[u];
+				s_wgt[xofs + jofs] = wgt;
+				s_x[xofs + jofs] = opG[u] * dL_dalpha;                        // q = dL/dG * G  (dL/dG = opacity * dL/dalpha)
+				T = Tk;                                                       // unchanged where the pair is skipped (rinv = 1)
+				S = fmaf(wgt, wdot, S);                                       // likewise (wgt = 0)
+			}
 		}
 		__syncwarp();
 		// ---- 4 + 5. GEMM 2: dC[g][ch] = wgt[g][:] . Gpx[:][ch];  GEMM 3: M[g][m] = q[g][:] . Y[:][m]   (K = pixels) ----
@@ -257,68 +265,56 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 #pragma unroll
 				for (int i = 0; i < 4; i++) dC[mt][nt][i] = 0.f;
 		}
-		{
-			// A fragments: rows g = 16 mt + 8 h + gid, logical columns 8 tig .. 8 tig + 7 = k-slots (ks, e) = (c >> 1, c & 1)
-			float wv[BWD_MT][2][8], qv[BWD_MT][2][8];
+#pragma unroll
+		for (int ks = 0; ks < 4; ks++) {
+			// A quads of wgt and q: pixel pair pi = 4 ks + tig, survivors 16 mt + 2 gid (+1)
+			uint32_t ahi[BWD_MT][4], alo[BWD_MT][4], qhi[BWD_MT][4], qlo[BWD_MT][4];
 #pragma unroll
 			for (int mt = 0; mt < BWD_MT; mt++) {
+				const float4 w4 = *reinterpret_cast<const float4*>(s_wgt + (4 * ks + tig) * XS + mt * 32 + gid * 4);
+				const float4 q4 = *reinterpret_cast<const float4*>(s_x + (4 * ks + tig) * XS + mt * 32 + gid * 4);
+				tf32_split(w4.x, ahi[mt][0], alo[mt][0]); tf32_split(w4.y, ahi[mt][1], alo[mt][1]);
+				tf32_split(w4.z, ahi[mt][2], alo[mt][2]); tf32_split(w4.w, ahi[mt][3], alo[mt][3]);
+				tf32_split(q4.x, qhi[mt][0], qlo[mt][0]); tf32_split(q4.y, qhi[mt][1], qlo[mt][1]);
+				tf32_split(q4.z, qhi[mt][2], qlo[mt][2]); tf32_split(q4.w, qhi[mt][3], qlo[mt][3]);
+			}
+			// B pairs of GEMM 2: cotangents of the pair's two pixels, channels NFT gid .. NFT gid + NFT - 1, then {r,g,b,depth}[gid]
+			const float* gp = s_g + (4 * ks + tig) * GS;
+			if (NFT > 0) {
+				float f[2 * (NFT > 0 ? NFT : 1)];
+				if (NFT == 4) {
+					const float4 u0 = *reinterpret_cast<const float4*>(gp + 8 * gid), u1 = *reinterpret_cast<const float4*>(gp + 8 * gid + 4);
+					f[0] = u0.x; f[1] = u0.y; f[2 % (2 * NFT)] = u0.z; f[3 % (2 * NFT)] = u0.w;
+					f[4 % (2 * NFT)] = u1.x; f[5 % (2 * NFT)] = u1.y; f[6 % (2 * NFT)] = u1.z; f[7 % (2 * NFT)] = u1.w;
+				} else if (NFT == 2) {
+					const float4 u0 = *reinterpret_cast<const float4*>(gp + 4 * gid);
+					f[0] = u0.x; f[1] = u0.y; f[2 % (2 * NFT)] = u0.z; f[3 % (2 * NFT)] = u0.w;
+				} else {
+					const float2 u0 = *reinterpret_cast<const float2*>(gp + 2 * gid);
+					f[0] = u0.x; f[1] = u0.y;
+				}
 #pragma unroll
-				for (int h = 0; h < 2; h++) {
-					const int g = 16 * mt + 8 * h + gid;
-					const int sw = 4 * (g & 1);
+				for (int nt = 0; nt < NFT; nt++) {
+					uint32_t bh0, bl0, bh1, bl1;
+					tf32_split(f[2 * nt], bh0, bl0);
+					tf32_split(f[2 * nt + 1], bh1, bl1);
 #pragma unroll
-					for (int u = 0; u < 2; u++) {
-						const float4 w4 = *reinterpret_cast<const float4*>(s_wgt + g * 32 + ((8 * tig + 4 * u) ^ sw));
-						const float4 q4 = *reinterpret_cast<const float4*>(s_x + g * 32 + ((8 * tig + 4 * u) ^ sw));
-						wv[mt][h][4 * u] = w4.x; wv[mt][h][4 * u + 1] = w4.y; wv[mt][h][4 * u + 2] = w4.z; wv[mt][h][4 * u + 3] = w4.w;
-						qv[mt][h][4 * u] = q4.x; qv[mt][h][4 * u + 1] = q4.y; qv[mt][h][4 * u + 2] = q4.z; qv[mt][h][4 * u + 3] = q4.w;
-					}
+					for (int mt = 0; mt < BWD_MT; mt++) mma_3xtf32(dC[mt][nt], ahi[mt], alo[mt], bh0, bh1, bl0, bl1);
 				}
 			}
+			{
+				const float2 c = *reinterpret_cast<const float2*>(gp + 2 * (RGBD + gid));  // columns 4..7 are the zero padding
+				uint32_t bh0, bl0, bh1, bl1;
+				tf32_split(c.x, bh0, bl0);
+				tf32_split(c.y, bh1, bl1);
 #pragma unroll
-			for (int ks = 0; ks < 4; ks++) {
-				uint32_t ahi[BWD_MT][4], alo[BWD_MT][4], qhi[BWD_MT][4], qlo[BWD_MT][4];
+				for (int mt = 0; mt < BWD_MT; mt++) mma_3xtf32(dC[mt][NFT], ahi[mt], alo[mt], bh0, bh1, bl0, bl1);
+			}
+			// GEMM 3: the basis is exact in TF32, only q is split
 #pragma unroll
-				for (int mt = 0; mt < BWD_MT; mt++) {
-#pragma unroll
-					for (int h = 0; h < 2; h++) {
-						tf32_split(wv[mt][h][2 * ks], ahi[mt][h], alo[mt][h]);              // k-slot (ks, tig)
-						tf32_split(wv[mt][h][2 * ks + 1], ahi[mt][2 + h], alo[mt][2 + h]);  // k-slot (ks, tig + 4)
-						tf32_split(qv[mt][h][2 * ks], qhi[mt][h], qlo[mt][h]);
-						tf32_split(qv[mt][h][2 * ks + 1], qhi[mt][2 + h], qlo[mt][2 + h]);
-					}
-				}
-				// B fragments of GEMM 2: cotangent rows of pixels p0 = 8 ks + 2 tig and p0 + 1
-				const float* g0 = s_g + (8 * ks + 2 * tig) * RS;
-				const float* g1 = g0 + RS;
-				if (NFT > 0) {
-					float f0[4], f1[4];
-					load_feat<NFT>(g0, gid, f0);
-					load_feat<NFT>(g1, gid, f1);
-#pragma unroll
-					for (int nt = 0; nt < NFT; nt++) {
-						uint32_t bh0, bl0, bh1, bl1;
-						tf32_split(f0[nt], bh0, bl0);
-						tf32_split(f1[nt], bh1, bl1);
-#pragma unroll
-						for (int mt = 0; mt < BWD_MT; mt++) mma_3xtf32(dC[mt][nt], ahi[mt], alo[mt], bh0, bh1, bl0, bl1);
-					}
-				}
-				{
-					const float c0 = gid < 4 ? g0[RGBD + gid] : 0.f;
-					const float c1 = gid < 4 ? g1[RGBD + gid] : 0.f;
-					uint32_t bh0, bl0, bh1, bl1;
-					tf32_split(c0, bh0, bl0);
-					tf32_split(c1, bh1, bl1);
-#pragma unroll
-					for (int mt = 0; mt < BWD_MT; mt++) mma_3xtf32(dC[mt][NFT], ahi[mt], alo[mt], bh0, bh1, bl0, bl1);
-				}
-				// GEMM 3: the basis is exact in TF32, only q is split
-#pragma unroll
-				for (int mt = 0; mt < BWD_MT; mt++) {
-					mma_tf32(mom[mt], qlo[mt][0], qlo[mt][1], qlo[mt][2], qlo[mt][3], ymom[ks][0], ymom[ks][1]);
-					mma_tf32(mom[mt], qhi[mt][0], qhi[mt][1], qhi[mt][2], qhi[mt][3], ymom[ks][0], ymom[ks][1]);
-				}
+			for (int mt = 0; mt < BWD_MT; mt++) {
+				mma_tf32(mom[mt], qlo[mt][0], qlo[mt][1], qlo[mt][2], qlo[mt][3], ymom[ks][0], ymom[ks][1]);
+				mma_tf32(mom[mt], qhi[mt][0], qhi[mt][1], qhi[mt][2], qhi[mt][3], ymom[ks][0], ymom[ks][1]);
 			}
 		}
 		__syncwarp();  // every lane has read its q fragments: s_x becomes the per-Gaussian staging area
@@ -329,7 +325,7 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 		for (int mt = 0; mt < BWD_MT; mt++) {
 #pragma unroll
 			for (int h = 0; h < 2; h++) {
-				const int g = 16 * mt + 8 * h + gid;
+				const int g = 16 * mt + 2 * gid + h;  // D rows gid (h = 0) and gid + 8 (h = 1)
 				if (tig < 3) *reinterpret_cast<float2*>(s_m + g * 12 + 2 * tig) = make_float2(mom[mt][2 * h], mom[mt][2 * h + 1]);
 				if (tig < 2) *reinterpret_cast<float2*>(s_m + g * 12 + 6 + 2 * tig) = make_float2(dC[mt][NFT][2 * h], dC[mt][NFT][2 * h + 1]);
 				if (NFT > 0 && g < cnt && a.dL_dfeat) {
@@ -388,11 +384,19 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 		__syncwarp();
 	};
 
-	for (int k = 0; k < nb; k++) {
-		const float4* rec4 = ring.wait(k);
-		const int lo = ring.batch_lo(k), n = ring.batch_n(k);
-		// chunks of the batch, back to front; survivors are appended in back-to-front order
-		for (int c = ((n - 1) >> 5) << 5; c >= 0; c -= 32) {
+	// Fill the queue from the record stream (back to front), run a chunk whenever BWD_CH survivors are queued, and the
+	// remainder at the end.  One call site for the chunk: the kernel's code stays within the instruction cache.
+	int k = 0, c = 0, lo = 0, n = 0;
+	const float4* rec4 = nullptr;
+	bool open = false;  // batch k is landed and partly culled
+	for (;;) {
+		while (qcount < BWD_CH && k < nb) {
+			if (!open) {
+				rec4 = ring.wait(k);
+				lo = ring.batch_lo(k); n = ring.batch_n(k);
+				c = ((n - 1) >> 5) << 5;  // chunks of the batch, back to front
+				open = true;
+			}
 			const int j = c + lane;
 			float4 r0, r1;
 			bool hit = false;
@@ -402,6 +406,7 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 			}
 			const uint32_t mask = __ballot_sync(0xffffffffu, hit);
 			if (hit) {
+				// survivors are appended in back-to-front order: the highest lane first
 				const uint32_t above = (lane == 31) ? 0u : (mask >> (lane + 1));
 				const int e = qcount + __popc(above);
 				r1.z = __uint_as_float((uint32_t)(lo + j) + 1u);  // the cull extent is spent: keep the 1-based list position instead
@@ -410,12 +415,17 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 			}
 			qcount += __popc(mask);
 			__syncwarp();
-			while (qcount >= BWD_CH) process_chunk(BWD_CH);
+			c -= 32;
+			if (c < 0) {
+				// every survivor of this batch sits in the queue: refill its buffer with the batch RING ahead
+				open = false;
+				if (issued < nb) { ring.issue(issued); issued++; }
+				k++;
+			}
 		}
-		// every survivor of this batch sits in the queue: refill its buffer with the batch RING ahead
-		if (issued < nb) { ring.issue(issued); issued++; }
+		if (qcount == 0) break;
+		process_chunk(min(qcount, BWD_CH));
 	}
-	if (qcount > 0) process_chunk(qcount);
 }
 
 bool feature_rows_vectorizable(const float* feature, int F);

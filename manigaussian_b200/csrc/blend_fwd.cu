@@ -17,11 +17,12 @@
 //                 m16n8k8 TF32, 3xTF32 split for fp32 accuracy, blend_mma.cuh), accumulators in the D fragments;
 //    the channel rows C of the chunk ({r,g,b,depth} quad + feature row, gathered by Gaussian id with 16-byte cp.async
 //    pieces, SASS LDGSTS) travel while the walk runs;
-//  * index assignment that makes every fragment access wide and conflict free: MMA row 16 mt + 8 h + gid is pixel
-//    (x = gid, y = 2 mt + h) = lane 4 gid + y of the walk, so a thread's four A values per survivor are one LDS.128 of
-//    the XOR-swizzled weight tile; column gid of feature tile nt is feature NFT*gid + nt, so a thread's B values per
-//    survivor are one LDS.128 of the channel row and its D fragments hold 2*NFT consecutive features of four pixels;
-//    with x = gid the output planes are written as full 32-byte sectors straight from the fragments.
+//  * index assignment that lets every MMA operand arrive in place (an A fragment is four consecutive registers, and a
+//    register move per fragment would cost more than the MMA saves): MMA row 16 mt + 8 h + gid is pixel (x = gid,
+//    y = 2 mt + h) = lane 4 gid + y of the walk, and the weight tile is stored per k-step as [tig][gid][mt][e][h]
+//    (survivor 8 ks + tig + 4 e), so {a0..a3} of one 16-pixel tile is ONE LDS.128 and the hi/lo split writes the second
+//    quad; the B pair {b0, b1} (survivors g0, g1, feature 8 nt + gid) is two conflict-free scalar loads of the channel rows;
+//    with x = gid the output planes are written as full 32-byte sectors straight from the D fragments.
 #include "blend_common.cuh"
 #include "blend_mma.cuh"
 
@@ -31,10 +32,10 @@ namespace mgs {
 #define MGS_FWD_CH 32
 #endif
 #ifndef MGS_FWD_MIN_CTAS
-#define MGS_FWD_MIN_CTAS 16
+#define MGS_FWD_MIN_CTAS 14
 #endif
 #ifndef MGS_FWD_BATCH
-#define MGS_FWD_BATCH 32
+#define MGS_FWD_BATCH 64
 #endif
 constexpr int FWD_CH = MGS_FWD_CH;        // survivors per tensor-core chunk (multiple of 8, <= 32)
 constexpr int FWD_QCAP = FWD_CH + 32;     // survivor queue: a chunk plus the survivors of one more 32-record cull
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 	__shared__ __align__(128) InstRec s_rec[RING * FWD_BATCH];
 	__shared__ __align__(16) float4 s_q[FWD_QCAP * 2];    // survivor queue, linear: {x,y,ca,cb}, {cc,op,pos,id}; the chunk is its head
 	__shared__ __align__(16) float s_rows[FWD_CH * RS];   // channel rows of the current chunk
-	__shared__ __align__(16) float s_w[FWD_CH * 32];      // blend weights [survivor][pixel ^ 8 (survivor & 3)]
+	__shared__ __align__(16) float s_w[FWD_CH * 32];      // blend weights, per k-step [tig][gid][mt][e][h]: survivor 8 ks + tig + 4 e, pixel 4 gid + 2 mt + h
 	__shared__ __align__(8) uint64_t s_bar[RING];
 
 	const int lane = threadIdx.x;
@@ -89,36 +90,26 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 			for (int i = 0; i < 4; i++) acc[mt][nt][i] = 0.f;
 
 	int qcount = 0;
-	const int lsw0 = lane, lsw1 = lane ^ 8, lsw2 = lane ^ 16, lsw3 = lane ^ 24;  // pixel column of the swizzled weight tile, by survivor & 3
-
-	// one survivor of the walk: returns this pixel's blend weight
-	auto blend_step = [&](bool act, const float4& p, const float4& q) -> float {
-		const float dx = p.x - pfx, dy = p.y - pfy;
-		const float power = -0.5f * (p.z * dx * dx + q.x * dy * dy) - p.w * dx * dy;
-		const float alpha = min(ALPHA_MAX, q.y * expf(power));
-		const bool cand = act && !done && !(power > 0.0f) && !(alpha < ALPHA_MIN);
-		const float test_T = T * (1 - alpha);
-		const bool stop = cand && (test_T < T_STOP);
-		const bool use = cand && !stop;
-		const float w = use ? alpha * T : 0.f;
-		done = done || stop;
-		T = use ? test_T : T;
-		last_contributor = use ? __float_as_uint(q.z) : last_contributor;
-		return w;
-	};
+	const int wofs = (lane >> 2) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1);  // this pixel's slot in a [tig][gid][mt][e][h] weight tile
 
 	// consume the first cnt (<= FWD_CH) queued survivors; returns true when every pixel of the block is finished
 	auto process_chunk = [&](int cnt) -> bool {
 		// ---- start the gather of the chunk's channel rows (lands while the walk runs) ----
 		if (VEC) {
-			constexpr int NPR = 2 * NFT + 1;  // 16-byte pieces per row: feature pieces, then {r,g,b,depth} at 4*(2 NFT) = L::RGBD
-			const int npieces = cnt * NPR;
-			for (int idx = lane; idx < npieces; idx += 32) {
-				const int r = idx / NPR, q = idx - r * NPR;
-				const uint32_t id = __float_as_uint(s_q[2 * r + 1].w);
-				const float4* src = (q == 2 * NFT) ? (a.rgbd + id) : (reinterpret_cast<const float4*>(a.feature + (size_t)id * F) + q);
-				cp_async16(s_rows + r * RS + 4 * q, src);
+			// lane r knows the Gaussian id of survivor r; the feature rows are cut into 16-byte pieces and 32 / (2 NFT) rows
+			// are copied per trip (lane = row-in-trip x piece), the id travelling by shuffle: 4 instructions per LDGSTS
+			const uint32_t myid = lane < cnt ? __float_as_uint(s_q[2 * lane + 1].w) : 0u;
+			if (NFT > 0) {
+				constexpr int NPF = NFT > 0 ? 2 * NFT : 1, RPI = 32 / NPF;  // pieces per feature row, rows per trip
+				const int sub = lane / NPF, q = lane % NPF;
+#pragma unroll
+				for (int it = 0; it < FWD_CH / RPI; it++) {
+					const int r = it * RPI + sub;
+					const uint32_t id = __shfl_sync(0xffffffffu, myid, r);
+					if (r < cnt) cp_async16(s_rows + r * RS + 4 * q, reinterpret_cast<const float4*>(a.feature + (size_t)id * (8 * NFT)) + q);
+				}
 			}
+			if (lane < cnt) cp_async16(s_rows + lane * RS + L::RGBD, a.rgbd + myid);
 			cp_async_commit();
 		} else if (lane < cnt) {  // feature rows that are not whole 8-wide tiles (e.g. F = 3): plain loads, zero padded
 			const uint32_t id = __float_as_uint(s_q[2 * lane + 1].w);
@@ -130,21 +121,38 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 				for (int i = 0; i < 8 * NFT; i++) row[i] = (i < F) ? __ldg(f + i) : 0.f;
 			}
 		}
-		// ---- walk: one k-step (8 survivors) per trip, two survivors per step (the second one's expf overlaps the
-		// first one's recurrence); slots beyond cnt hold stale records and get zero weights ----
+		// ---- walk: one k-step (8 survivors) per trip, in two passes so that the eight footprint evaluations (independent:
+		// LDS, 8 FP ops, expf) overlap in the pipeline and only the short transmittance recurrence is sequential.
+		// Slots beyond cnt hold stale records and get zero weights. ----
 		const int nks = (cnt + 7) >> 3;
 		int ks = 0;
 		for (; ks < nks; ks++) {
 			if (ks > 0 && __all_sync(0xffffffffu, done)) break;
 			const float4* q4 = s_q + 16 * ks;
 			float* wrow = s_w + 256 * ks;
+			float al[8];      // alpha of the pair, 0 where the pair is skipped (power > 0, alpha < 1/255, empty slot)
+			uint32_t ps[8];   // 1-based position of the survivor in the tile's list
 #pragma unroll
-			for (int u = 0; u < 8; u += 2) {
-				const float4 p0 = q4[2 * u], q0 = q4[2 * u + 1], p1 = q4[2 * u + 2], q1 = q4[2 * u + 3];
-				const float w0 = blend_step(8 * ks + u < cnt, p0, q0);
-				const float w1 = blend_step(8 * ks + u + 1 < cnt, p1, q1);
-				wrow[u * 32 + ((u & 3) == 0 ? lsw0 : lsw2)] = w0;
-				wrow[(u + 1) * 32 + (((u + 1) & 3) == 1 ? lsw1 : lsw3)] = w1;
+			for (int u = 0; u < 8; u++) {
+				const float4 p = q4[2 * u], q = q4[2 * u + 1];
+				const float dx = p.x - pfx, dy = p.y - pfy;
+				const float power = -0.5f * (p.z * dx * dx + q.x * dy * dy) - p.w * dx * dy;
+				const float alpha = min(ALPHA_MAX, q.y * expf(power));
+				const bool ok = (8 * ks + u < cnt) && !(power > 0.0f) && !(alpha < ALPHA_MIN);
+				al[u] = ok ? alpha : 0.f;
+				ps[u] = __float_as_uint(q.z);
+			}
+#pragma unroll
+			for (int u = 0; u < 8; u++) {
+				const float alpha = al[u];
+				const bool cand = !done && (alpha != 0.f);
+				const float test_T = T * (1 - alpha);
+				const bool stop = cand && (test_T < T_STOP);
+				const bool use = cand && !stop;
+				wrow[(u & 3) * 64 + (u >> 2) * 2 + wofs] = use ? alpha * T : 0.f;
+				done = done || stop;
+				T = use ? test_T : T;
+				last_contributor = use ? ps[u] : last_contributor;
 			}
 		}
 		const int nk = ks;  // k-steps to contract
@@ -153,28 +161,25 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 		// ---- contract on the tensor cores ----
 		for (int ks = 0; ks < nk; ks++) {
 			const int g0 = 8 * ks + tig, g1 = g0 + 4;
-			// pixels 4 gid .. 4 gid + 3 of survivor g: one 16-byte group of the swizzled tile
-			const float4 wa = *reinterpret_cast<const float4*>(s_w + g0 * 32 + ((4 * gid) ^ (8 * (g0 & 3))));
-			const float4 wb = *reinterpret_cast<const float4*>(s_w + g1 * 32 + ((4 * gid) ^ (8 * (g1 & 3))));
+			// {a0..a3} of pixel tile mt: weights of survivors g0 (k = tig) and g1 (k = tig + 4) at pixels 4 gid + 2 mt + {0, 1}
+			const float4 wa = *reinterpret_cast<const float4*>(s_w + ks * 256 + tig * 64 + gid * 8);
+			const float4 wb = *reinterpret_cast<const float4*>(s_w + ks * 256 + tig * 64 + gid * 8 + 4);
 			uint32_t ahi[2][4], alo[2][4];
 			tf32_split(wa.x, ahi[0][0], alo[0][0]); tf32_split(wa.y, ahi[0][1], alo[0][1]);
-			tf32_split(wb.x, ahi[0][2], alo[0][2]); tf32_split(wb.y, ahi[0][3], alo[0][3]);
-			tf32_split(wa.z, ahi[1][0], alo[1][0]); tf32_split(wa.w, ahi[1][1], alo[1][1]);
+			tf32_split(wa.z, ahi[0][2], alo[0][2]); tf32_split(wa.w, ahi[0][3], alo[0][3]);
+			tf32_split(wb.x, ahi[1][0], alo[1][0]); tf32_split(wb.y, ahi[1][1], alo[1][1]);
 			tf32_split(wb.z, ahi[1][2], alo[1][2]); tf32_split(wb.w, ahi[1][3], alo[1][3]);
 			const float* row0 = s_rows + g0 * RS;
 			const float* row1 = s_rows + g1 * RS;
-			if (NFT > 0) {
-				float f0[4], f1[4];
-				load_feat<NFT>(row0, gid, f0);
-				load_feat<NFT>(row1, gid, f1);
+			// B fragments {b0, b1} = column gid of tile nt for survivors g0 and g1: scalar, conflict-free loads straight into
+			// the operand pair (a 128-bit row load would need a register move per operand)
 #pragma unroll
-				for (int nt = 0; nt < NFT; nt++) {
-					uint32_t bh0, bl0, bh1, bl1;
-					tf32_split(f0[nt], bh0, bl0);
-					tf32_split(f1[nt], bh1, bl1);
-					mma_3xtf32(acc[0][nt], ahi[0], alo[0], bh0, bh1, bl0, bl1);
-					mma_3xtf32(acc[1][nt], ahi[1], alo[1], bh0, bh1, bl0, bl1);
-				}
+			for (int nt = 0; nt < NFT; nt++) {
+				uint32_t bh0, bl0, bh1, bl1;
+				tf32_split(row0[8 * nt + gid], bh0, bl0);
+				tf32_split(row1[8 * nt + gid], bh1, bl1);
+				mma_3xtf32(acc[0][nt], ahi[0], alo[0], bh0, bh1, bl0, bl1);
+				mma_3xtf32(acc[1][nt], ahi[1], alo[1], bh0, bh1, bl0, bl1);
 			}
 			{
 				const float c0 = gid < 4 ? row0[L::RGBD + gid] : 0.f;
@@ -197,12 +202,20 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 		return __all_sync(0xffffffffu, done);
 	};
 
-	bool finished = false;
-	for (int k = 0; k < nb && !finished; k++) {
-		const float4* rec4 = ring.wait(k);
-		waited = k + 1;
-		const int lo = ring.batch_lo(k), n = ring.batch_n(k);
-		for (int c = 0; c < n && !finished; c += 32) {
+	// Fill the queue from the record stream, run a chunk whenever FWD_CH survivors are queued, and the remainder at the
+	// end.  One call site for the chunk: the kernel's code stays within the instruction cache.
+	int k = 0, c = 0, lo = 0, n = 0;
+	const float4* rec4 = nullptr;
+	bool open = false;  // batch k is landed and partly culled
+	for (;;) {
+		while (qcount < FWD_CH && k < nb) {
+			if (!open) {
+				rec4 = ring.wait(k);
+				waited = k + 1;
+				lo = ring.batch_lo(k); n = ring.batch_n(k);
+				c = 0;
+				open = true;
+			}
 			const int j = c + lane;
 			float4 r0, r1;
 			bool hit = false;
@@ -219,12 +232,17 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 			}
 			qcount += __popc(mask);
 			__syncwarp();
-			while (qcount >= FWD_CH && !finished) finished = process_chunk(FWD_CH);
+			c += 32;
+			if (c >= n) {
+				// every survivor of this batch sits in the queue: its buffer is free for the batch RING ahead
+				open = false;
+				if (issued < nb) { ring.issue(issued); issued++; }
+				k++;
+			}
 		}
-		// every survivor of this batch sits in the queue: its buffer is free for the batch RING ahead
-		if (!finished && issued < nb) { ring.issue(issued); issued++; }
+		if (qcount == 0) break;
+		if (process_chunk(min(qcount, FWD_CH))) break;  // every pixel of the block is finished
 	}
-	if (!finished && qcount > 0) process_chunk(qcount);
 	for (int k = waited; k < issued; k++) ring.wait(k);  // no bulk copy may be in flight when the CTA exits
 
 	// ---- outputs ----
@@ -250,7 +268,7 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 				for (int nt = 0; nt < NFT; nt++) {
 #pragma unroll
 					for (int e = 0; e < 2; e++) {
-						const int f = NFT * (2 * tig + e) + nt;
+						const int f = 8 * nt + 2 * tig + e;
 						if (f < F) a.out_feature[(size_t)f * HW + pix] = acc[mt][nt][2 * h + e];
 					}
 				}
