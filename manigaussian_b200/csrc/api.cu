@@ -16,7 +16,6 @@
 #include "mgs_kernels.h"
 
 namespace mgs {
-int nq_for(int F);
 
 static thread_local std::string g_err;
 
@@ -150,15 +149,6 @@ static size_t required(F carve)
 	carve(p);
 	return reinterpret_cast<size_t>(p) + 128;
 }
-int blend_variant()
-{
-	static const int v = [] {
-		const char* e = getenv("MGS_BLEND");
-		const std::string s = e ? e : "";
-		return s == "simt" ? 3 : s == "simt_fwd" ? 1 : s == "simt_bwd" ? 2 : 0;
-	}();
-	return v;
-}
 static size_t num_tiles(int W, int H) { return (size_t)ceil_div(W, TILE_X) * ceil_div(H, TILE_Y); }
 
 // next-highest bit of the MSB (number of bits needed for tile ids); same result as the reference's
@@ -277,7 +267,7 @@ static int forward_phase2(
 	}
 	{
 		StageTimer t_(ST_RANGES_PACK, st);
-		launch_ranges_and_pack(num_rendered, (int)T, bin.tile_keys, bin.point_list, geom.means2D, geom.conic_opacity, geom.extent,
+		launch_ranges_and_pack(num_rendered, (int)T, gx, bin.tile_keys, bin.point_list, geom.means2D, geom.conic_opacity, geom.extent,
 			img.ranges, bin.recs, st);
 	}
 	MGS_STAGE("ranges_pack");
@@ -285,7 +275,7 @@ static int forward_phase2(
 	if (!(stages & 2)) return num_rendered;
 
 	BlendArgs ba{};
-	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F; ba.nq = nq_for(F);
+	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F;
 	ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
 	ba.rgbd = geom.rgbd; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
 	ba.want_depth = out_depth != nullptr;
@@ -409,7 +399,7 @@ int mgs_backward(
 	if (F > 0 && !accumulate) MGS_CUDA(cudaMemsetAsync(dL_dfeature, 0, (size_t)P * F * sizeof(float), st));
 
 	BlendArgs ba{};
-	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F; ba.nq = nq_for(F);
+	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F;
 	ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
 	ba.rgbd = geom.rgbd; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
 	ba.want_depth = dL_dpix_depth != nullptr;

@@ -14,7 +14,6 @@
 // reference; BASELINE.json's north_star asks for "cub-style radix sort").  The emit and ranges+pack kernels are
 // hand-written; the latter also gathers the per-instance 32-byte blend record into tile order, so the blend kernels
 // fetch a tile's work list with 1-D TMA bulk copies (the reference gathers by index inside the blend).
-#include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -104,8 +103,46 @@ void launch_tile_sort(void* temp, size_t temp_bytes, const uint32_t* keys_in, ui
 	cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, R, 0, end_bit, s);
 }
 
+// Which of the eight 8x4 pixel blocks of tile (tx, ty) can the footprint {alpha >= 1/255} of a Gaussian reach?
+// alpha = min(0.99, o exp(-q/2)), q(d) = ca dx^2 + 2 cb dx dy + cc dy^2, d = mean - pixel: the pair can contribute iff
+// q(d) <= 2 ln(255 o) =: 2 tau.  Per block the minimum of q over the rectangle of its pixel centres is compared with
+// 2 tau (exact up to the slack folded into tau): 0 if the mean lies inside, else the smallest of the four edge minima
+// (a convex quadratic restricted to a segment).  ext = the axis-aligned half-extent from the projection kernel
+// (-1: never contributes, 1e30: conic degenerate, do not cull), used as the cheap first test.
+__device__ __forceinline__ uint32_t block_mask(float gx, float gy, float ca, float cb, float cc, float op, float2 ext, int tx, int ty)
+{
+	if (ext.x < 0.f) return 0u;
+	if (ext.x > 1e29f) return 0xffu;
+	const float tau2 = 2.0f * (logf(255.0f * op) * 1.0005f + 1e-3f);  // same slack as the extent (project.cu)
+	const float icc = 1.0f / cc, ica = 1.0f / ca;                      // ca, cc > 0 whenever ext is finite
+	uint32_t mask = 0;
+#pragma unroll
+	for (int s = 0; s < 8; s++) {
+		const float x0 = (float)(tx * TILE_X + (s & 1) * WARP_BX), x1 = x0 + (float)(WARP_BX - 1);
+		const float y0 = (float)(ty * TILE_Y + (s >> 1) * WARP_BY), y1 = y0 + (float)(WARP_BY - 1);
+		if (!((gx + ext.x >= x0) && (gx - ext.x <= x1) && (gy + ext.y >= y0) && (gy - ext.y <= y1))) continue;
+		// d ranges over [dxl, dxh] x [dyl, dyh]
+		const float dxl = gx - x1, dxh = gx - x0, dyl = gy - y1, dyh = gy - y0;
+		float qmin = 0.f;
+		if (!(dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f)) {
+			qmin = 3.0e38f;
+#pragma unroll
+			for (int e = 0; e < 2; e++) {
+				const float X = e ? dxh : dxl;
+				const float dy = fminf(fmaxf(-cb * X * icc, dyl), dyh);
+				qmin = fminf(qmin, ca * X * X + 2.0f * cb * X * dy + cc * dy * dy);
+				const float Y = e ? dyh : dyl;
+				const float dx = fminf(fmaxf(-cb * Y * ica, dxl), dxh);
+				qmin = fminf(qmin, ca * dx * dx + 2.0f * cb * dx * Y + cc * Y * Y);
+			}
+		}
+		if (qmin <= tau2 * 1.0001f + 1e-4f) mask |= 1u << s;
+	}
+	return mask;
+}
+
 // One thread per sorted instance: tile boundary detection + gather of the 32-byte blend record.
-__global__ void __launch_bounds__(256) ranges_pack_kernel(int R, const uint32_t* __restrict__ tile_keys,
+__global__ void __launch_bounds__(256) ranges_pack_kernel(int R, int grid_x, const uint32_t* __restrict__ tile_keys,
 	const uint32_t* __restrict__ point_list, const float2* __restrict__ means2D,
 	const float4* __restrict__ conic_opacity, const float2* __restrict__ extent,
 	uint2* __restrict__ ranges, InstRec* __restrict__ recs)
@@ -128,18 +165,17 @@ __global__ void __launch_bounds__(256) ranges_pack_kernel(int R, const uint32_t*
 	const float2 xy = means2D[g];
 	const float4 co = conic_opacity[g];
 	const float2 ex = extent[g];
-	// extents travel as half2, rounded UP so the cull stays conservative (1e30 -> +inf = "never cull")
-	const __half2 eh = __halves2half2(__float2half_ru(ex.x), __float2half_ru(ex.y));
+	const uint32_t mask = block_mask(xy.x, xy.y, co.x, co.y, co.z, co.w, ex, (int)(currtile % (uint32_t)grid_x), (int)(currtile / (uint32_t)grid_x));
 	float4* dst = reinterpret_cast<float4*>(recs + idx);
 	dst[0] = make_float4(xy.x, xy.y, co.x, co.y);
-	dst[1] = make_float4(co.z, co.w, __uint_as_float(*reinterpret_cast<const uint32_t*>(&eh)), __uint_as_float(g));
+	dst[1] = make_float4(co.z, co.w, __uint_as_float(mask), __uint_as_float(g));
 }
 
-void launch_ranges_and_pack(int R, int num_tiles, const uint32_t* tile_keys, const uint32_t* point_list,
+void launch_ranges_and_pack(int R, int num_tiles, int grid_x, const uint32_t* tile_keys, const uint32_t* point_list,
 	const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs, cudaStream_t s)
 {
 	cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s);
-	if (R > 0) ranges_pack_kernel<<<ceil_div(R, 256), 256, 0, s>>>(R, tile_keys, point_list, means2D, conic_opacity, extent, ranges, recs);
+	if (R > 0) ranges_pack_kernel<<<ceil_div(R, 256), 256, 0, s>>>(R, grid_x, tile_keys, point_list, means2D, conic_opacity, extent, ranges, recs);
 }
 
 }  // namespace mgs

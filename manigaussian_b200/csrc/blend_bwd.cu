@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 	const int by0 = tile_y * TILE_Y + (sub >> 1) * WARP_BY;
 	const int pxi = bx0 + (lane >> 2), pyi = by0 + (lane & 3);  // walk role: lane = pixel (x = lane >> 2, y = lane & 3)
 	const bool inside = pxi < a.W && pyi < a.H;
-	const float fbx0 = (float)bx0, fbx1 = (float)(bx0 + WARP_BX - 1), fby0 = (float)by0, fby1 = (float)(by0 + WARP_BY - 1);
+	const float fbx0 = (float)bx0, fby0 = (float)by0;
 	const size_t HW = (size_t)a.H * a.W;
 	const size_t pix = (size_t)a.W * pyi + pxi;
 	const int F = a.F;
@@ -401,8 +401,9 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 			float4 r0, r1;
 			bool hit = false;
 			if (j < n) {
-				r0 = rec4[2 * j]; r1 = rec4[2 * j + 1];
-				hit = rec_hits_block(r0, r1, fbx0, fbx1, fby0, fby1);
+				r1 = rec4[2 * j + 1];
+				hit = rec_hits_block(r1, sub);
+				if (hit) r0 = rec4[2 * j];
 			}
 			const uint32_t mask = __ballot_sync(0xffffffffu, hit);
 			if (hit) {
@@ -429,7 +430,6 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 }
 
 bool feature_rows_vectorizable(const float* feature, int F);
-void launch_blend_bwd_simt(const BlendArgs& a, cudaStream_t s);
 
 template <int NFT>
 static void launch_bwd_t(const BlendArgs& a, cudaStream_t s)
@@ -443,7 +443,6 @@ static void launch_bwd_t(const BlendArgs& a, cudaStream_t s)
 
 void launch_blend_bwd(const BlendArgs& a, cudaStream_t s)
 {
-	if (blend_variant() & 2) { launch_blend_bwd_simt(a, s); return; }
 	switch (nft_for(a.F)) {
 	case 0: launch_bwd_t<0>(a, s); break;
 	case 1: launch_bwd_t<1>(a, s); break;

@@ -3,41 +3,27 @@
 // Work decomposition: ONE WARP = ONE CTA = one 8x4 pixel block of a 16x16 tile (tile ids / work lists stay the
 // reference's 16x16 tiles; eight single-warp CTAs share a tile's list).  A warp streams the tile's sorted 32-byte
 // instance records through its own RING-deep shared-memory ring with 1-D TMA bulk copies (SASS UBLKCP), one copy per
-// batch of REC_BATCH records tracked by an mbarrier, culls each 32-record chunk against its pixel block, and works
-// on the survivors.  No CTA-wide barrier exists anywhere: warps of a heavy tile never wait for each other, finished
-// warps free their SM slot immediately, and the hardware scheduler balances the 8*T*V small CTAs across the 148 SMs.
+// batch of records tracked by an mbarrier, keeps the records whose footprint reaches its block (one bit per block in the
+// record, set by the binning stage) and works on the survivors.  No CTA-wide barrier exists anywhere: warps of a heavy
+// tile never wait for each other, finished warps free their SM slot immediately, and the hardware scheduler balances
+// the 8*T*V small CTAs across the 148 SMs.
 #pragma once
-#include <cuda_fp16.h>
 #include "mgs_common.cuh"
 #include "mgs_kernels.h"
 
 namespace mgs {
 
-constexpr int REC_BATCH = 64;  // records per bulk copy of the round-1 SIMT kernels (2 KB) = two 32-record chunks
 #ifndef MGS_RING
 #define MGS_RING 2
 #endif
-// record batches in flight / resident per warp.  2 beats 3 and 4 at c3 (3.74 vs 3.88 vs 3.93 ms per 4-view step): the kernels'
-// own times do not change, but the smaller footprint lets more CTAs of concurrently running views share an SM.
+// record batches in flight / resident per warp
 constexpr int RING = MGS_RING;
 
-// {x, y, ca, cb} and {cc, op, ext(half2 hx,hy), id} views of a record
-__device__ __forceinline__ float2 rec_extent(const float4& r1)
-{
-	return __half22float2(*reinterpret_cast<const __half2*>(&r1.z));
-}
+// {x, y, ca, cb} and {cc, op, block mask, id} views of a record
 __device__ __forceinline__ uint32_t rec_id(const float4& r1) { return __float_as_uint(r1.w); }
-
-// does the alpha >= 1/255 footprint of the record overlap the pixel block [x0,x1] x [y0,y1]?  Axis-aligned extent of the
-// footprint ellipse against the block; conservative.  (The exact ellipse-vs-rectangle test -- minimum of the conic's
-// quadratic form over the block against the level 2 ln(255 o) -- removes another 8-12 % of the survivors, but its ~25
-// instructions on the per-chunk critical path cost what the survivors save: forward 0.372 -> 0.388 ms, backward 0.528
-// -> 0.522 ms per c3 view.  Not kept.)
-__device__ __forceinline__ bool rec_hits_block(const float4& r0, const float4& r1, float x0, float x1, float y0, float y1)
-{
-	const float2 e = rec_extent(r1);
-	return (e.x >= 0.f) && (r0.x + e.x >= x0) && (r0.x - e.x <= x1) && (r0.y + e.y >= y0) && (r0.y - e.y <= y1);
-}
+// can the record contribute to 8x4 block `sub` (0..7, row-major 2 x 4) of its tile?  Decided once per instance by the
+// binning stage (exact ellipse-vs-block test of the alpha >= 1/255 footprint, binning.cu); conservative, never changes a pixel.
+__device__ __forceinline__ bool rec_hits_block(const float4& r1, int sub) { return (__float_as_uint(r1.z) >> sub) & 1u; }
 
 // Per-warp record ring of BATCH-record buffers.  All methods are called by the whole (converged) warp.
 template <int BATCH>
@@ -81,6 +67,5 @@ struct WarpRecRingT {
 	}
 	__device__ __forceinline__ const float4* buffer(int k) const { return reinterpret_cast<const float4*>(buf + (k % RING) * BATCH); }
 };
-using WarpRecRing = WarpRecRingT<REC_BATCH>;
 
 }  // namespace mgs

@@ -65,7 +65,6 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 	const bool inside = pxi < a.W && pyi < a.H;
 	if (__all_sync(0xffffffffu, !inside)) return;  // block entirely outside the image (ragged right/bottom tiles)
 	const float pfx = (float)pxi, pfy = (float)pyi;
-	const float fbx0 = (float)bx0, fbx1 = (float)(bx0 + WARP_BX - 1), fby0 = (float)by0, fby1 = (float)(by0 + WARP_BY - 1);
 	const int F = a.F;
 
 	// rows beyond a short last chunk are multiplied by zero weights: they must hold finite numbers
@@ -220,8 +219,9 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 			float4 r0, r1;
 			bool hit = false;
 			if (j < n) {
-				r0 = rec4[2 * j]; r1 = rec4[2 * j + 1];
-				hit = rec_hits_block(r0, r1, fbx0, fbx1, fby0, fby1);
+				r1 = rec4[2 * j + 1];
+				hit = rec_hits_block(r1, sub);
+				if (hit) r0 = rec4[2 * j];
 			}
 			const uint32_t mask = __ballot_sync(0xffffffffu, hit);
 			if (hit) {
@@ -302,11 +302,9 @@ static void launch_fwd_t(const BlendArgs& a, cudaStream_t s)
 	else blend_fwd_kernel<NFT, false><<<grid, 32, 0, s>>>(a);
 }
 
-void launch_blend_fwd_simt(const BlendArgs& a, cudaStream_t s);
 
 void launch_blend_fwd(const BlendArgs& a, cudaStream_t s)
 {
-	if (blend_variant() & 1) { launch_blend_fwd_simt(a, s); return; }
 	switch (nft_for(a.F)) {
 	case 0: launch_fwd_t<0>(a, s); break;
 	case 1: launch_fwd_t<1>(a, s); break;

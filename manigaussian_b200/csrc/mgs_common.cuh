@@ -27,8 +27,8 @@ struct __align__(16) InstRec {
 	float x, y;        // pixel-space mean (geom means2D)
 	float ca, cb;      // conic.x, conic.y
 	float cc, op;      // conic.z, opacity
-	uint32_t ext;      // half2 {hx, hy}: conservative (rounded up) half-extent of the alpha >= 1/255 footprint;
-	                   // -1 = never contributes, +inf = unknown (never cull).  Cull only, never changes a pixel.
+	uint32_t blocks;   // bit s: the alpha >= 1/255 footprint can reach 8x4 pixel block s of the instance's tile
+	                   // (s = 2 * (y / 4) + x / 8).  Conservative; cull only, never changes a pixel.
 	uint32_t id;       // Gaussian index (== point_list entry)
 };
 static_assert(sizeof(InstRec) == 32, "InstRec must be 32 bytes");

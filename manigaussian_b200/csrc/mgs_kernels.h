@@ -71,7 +71,6 @@ struct BlendArgs {
 	int W, H;
 	int grid_x, grid_y;
 	int F;                       // user feature channels (0 = none)
-	int nq;                      // float4 groups per channel row: ceil((4 + F) / 4)
 	const uint2* ranges;         // [T]
 	const uint32_t* point_list;  // [R] sorted Gaussian ids
 	const InstRec* recs;         // [R] sorted packed records
@@ -137,13 +136,11 @@ void launch_emit_tiles(int P, const uint32_t* order, const float2* means2D, cons
 	uint32_t grid_x, uint32_t grid_y, uint32_t* tile_keys, uint32_t* values, cudaStream_t s);
 void launch_tile_sort(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
 	const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit, cudaStream_t s);
-void launch_ranges_and_pack(int R, int num_tiles, const uint32_t* tile_keys, const uint32_t* point_list,
+void launch_ranges_and_pack(int R, int num_tiles, int grid_x, const uint32_t* tile_keys, const uint32_t* point_list,
 	const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs, cudaStream_t s);
 
 // blend_fwd.cu / blend_bwd.cu
 int blend_supported(int F);
-int blend_variant();  // bit 0 / bit 1: use the round-1 SIMT forward / backward blend (MGS_BLEND=simt|simt_fwd|simt_bwd; A/B measurements only)
-int nq_for(int F);
 void launch_blend_fwd(const BlendArgs& a, cudaStream_t s);
 void launch_blend_bwd(const BlendArgs& a, cudaStream_t s);
 
