@@ -216,34 +216,25 @@ def make_packed(P, F, M, torch):
 
 
 def run_step_views(G, C, T, flat, acc, dist, F, depth):
-    """ours, multi-view entry points: all views' projection/binning chains are in flight before the host waits for the first
-    instance count; blends of different views overlap (manigaussian_b200.rasterizer.rasterize_views_raw)."""
-    import torch
+    """ours, multi-view entry points: ONE C call enqueues every view's forward on its own stream, one more every view's
+    backward, neither synchronises with the host (manigaussian_b200.rasterizer.rasterize_views_raw); the backward sums the
+    per-Gaussian gradients of all views in registers and writes them ONCE into the packed buffer -- the all-reduce message."""
     from manigaussian_b200 import rasterizer as R
     from manigaussian_b200 import GaussianRasterizationSettings as S
     if "settings" not in G:
         G["settings"] = [S(c["H"], c["W"], c["tanfovx"], c["tanfovy"], c["bg"], 1.0, c["viewmatrix"], c["projmatrix"], SH_DEGREE,
                            c["campos"], False, False, F > 0) for c in C]
     views = G["settings"]
-    flat.zero_()
     outs, sts = R.rasterize_views_raw(views, G["means3D"], G["empty"], G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0,
                                       G["empty"], G["shs"], SH_DEGREE, F > 0, return_depth=depth)
-    # every view's backward ADDS its gradients straight into the packed buffer (the all-reduce message): no per-view
-    # gradient tensors, no elementwise accumulation kernels
     R.rasterize_views_backward_raw(views, outs, sts, [t["dL_dcolor"] for t in T],
                                    [t["dL_dfeature"] for t in T] if F else None, G["means3D"], G["empty"], G["feature"],
                                    G["scales"], G["rotations"], 1.0, G["empty"], G["shs"], SH_DEGREE, F > 0,
                                    grads_depth=[t["dL_ddepth"] for t in T] if depth else None, accumulate_into=acc)
-    main = torch.cuda.current_stream()
-    Rs = 0
-    for o in outs:
-        Rs += int(o[0])
-        for t in o:
-            if hasattr(t, "record_stream"):
-                t.record_stream(main)
     if dist is not None:
         dist.all_reduce(flat)
-    return Rs
+    G["last_outs"] = outs  # instance counts are read after the timed region (no host synchronisation inside it)
+    return 0
 
 
 def run_step(impl, G, C, T, flat, acc, dist=None, streams=None):
@@ -302,39 +293,27 @@ def make_render(impl_name, wl, torch):
         Fb = 32 if need > 3 else 3
         mod = util.load_reference(Fb)
 
-        class _Fn(torch.autograd.Function):  # mirrors DGR/diff_gaussian_rasterization/__init__.py:46-164 around the reference's _C
-            @staticmethod
-            def forward(ctx, means3D, means2D, sh, feat, opac, scales, rots, st):
-                e = torch.Tensor([])
-                n, color, lf, radii, gb, bb, ib = mod.rasterize_gaussians(st.bg, means3D, e, feat, opac, scales, rots, 1.0, e,
-                                                                          st.viewmatrix, st.projmatrix, st.tanfovx, st.tanfovy,
-                                                                          st.image_height, st.image_width, sh, st.sh_degree,
-                                                                          st.campos, False, False, True)
-                ctx.st, ctx.n = st, n
-                ctx.save_for_backward(feat, means3D, scales, rots, radii, sh, gb, bb, ib)
-                return color, lf, radii
-
-            @staticmethod
-            def backward(ctx, gc, gf, _):
-                st = ctx.st
-                feat, means3D, scales, rots, radii, sh, gb, bb, ib = ctx.saved_tensors
-                e = torch.Tensor([])
-                g = mod.rasterize_gaussians_backward(st.bg, means3D, radii, e, feat, scales, rots, 1.0, e, st.viewmatrix,
-                                                     st.projmatrix, st.tanfovx, st.tanfovy, gc.contiguous(), gf.contiguous(), sh,
-                                                     st.sh_degree, st.campos, gb, ctx.n, bb, ib, False, True)
-                return g[4], g[0], g[6], g[2], g[3], g[7], g[8], None
+        pkg = util.load_reference_package(Fb)  # the reference's OWN diff_gaussian_rasterization/__init__.py around its compiled _C
+        if pkg is None:
+            raise RuntimeError("oracle/_ref/python (the reference's Python operator) is missing: run oracle/build_ref.py")
 
         def render(st, means3D, means2D, opacities, shs, language_feature_precomp, scales, rotations):
-            feat = torch.zeros((P, Fb), device="cuda")
             k = 0
-            if F:
-                feat = torch.cat([language_feature_precomp, feat[:, F:]], 1)
-                k = F
+            if F == Fb and not wl["depth"]:
+                feat = language_feature_precomp  # the build's width: handed over as is
+            else:
+                feat = torch.zeros((P, Fb), device="cuda")
+                if F:
+                    feat = torch.cat([language_feature_precomp, feat[:, F:]], 1)
+                    k = F
             if wl["depth"]:
                 vm = st.viewmatrix.reshape(-1)
                 z = means3D @ torch.stack([vm[2], vm[6], vm[10]]) + vm[14]
                 feat = torch.cat([feat[:, :k], z[:, None], feat[:, k + 1:]], 1)
-            color, lf, radii = _Fn.apply(means3D, means2D, shs, feat, opacities, scales, rotations, st)
+            rst = pkg.GaussianRasterizationSettings(*st)  # same 13 fields, in the reference's own NamedTuple
+            color, lf, radii = pkg.GaussianRasterizer(raster_settings=rst)(
+                means3D=means3D, means2D=means2D, shs=shs, colors_precomp=None, language_feature_precomp=feat, opacities=opacities,
+                scales=scales, rotations=rotations, cov3D_precomp=None)
             if wl["depth"]:
                 return color, lf[:F], radii, lf[F]
             return color, lf[:F], radii
@@ -574,10 +553,11 @@ def main_dyna(a, wl, base, cfg, torch, rank, world):
     ms_step = e0.elapsed_time(e1) / a.steps
     units = P * 2 * V
     out = dict(base, value=units / (ms_step * 1e-3), ms_per_step=ms_step, clocks=clocks)
-    cfg.update(gaussian_views_per_step=2 * V, loss=float(loss.item()),
-               grads_checked={k: bool(torch.isfinite(v.grad).all().item()) for k, v in L.items() if v.requires_grad},
-               l2="no flush: per-step working set exceeds the 126 MB L2")
+    cfg.update(gaussian_views_per_step=2 * V, l2="no flush: per-step working set exceeds the 126 MB L2")
+    meas = dict(loss=float(loss.item()),
+                grads_checked={k: bool(torch.isfinite(v.grad).all().item()) for k, v in L.items() if v.requires_grad})
     out["config"] = cfg
+    out["measured"] = meas
     if not a.no_e2e:
         copy_stream = torch.cuda.Stream()
 
@@ -628,7 +608,7 @@ def main_dyna(a, wl, base, cfg, torch, rank, world):
         st = _binding.profile_read()
         _binding.profile_enable(False)
         per = {k: v[0] / max(v[1], 1) for k, v in st.items()}
-        cfg["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
+        meas["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
         # algorithmic bytes of the two launches per direction (current frame: all fields + F features; next frame: no features)
         small = 4 * (3 + 4 + 3 + 1)
         fwd_b = P * ((small + 12 + 4 * F) + (small + 4 * F)) + P * ((small + 12 + 16 + 12) + small)
@@ -692,6 +672,70 @@ def cpu_baseline(wl, target_s=12.0):
                       f"(probe: {probe_n} Gaussians in {probe:.2f} s)"}, total
 
 
+# ------------------------------------------------------------------------------------------------ c5: strong scaling
+def strong_scaling_c5(torch, dist, rank, world, steps, warmup):
+    """BASELINE.json configs[4] / north_star's multi-GPU split: 1M Gaussians (replicated), 8 views 256x256 with 32 feature
+    channels sharded round-robin over the ranks (view v on rank v % world: one view per GPU at 8 GPUs), ONE all-reduce of the
+    packed per-Gaussian gradient buffer per step.  Strong scaling: the 8 views are fixed, `value` = P * 8 / step time.
+    Also checks the exchange: the all-reduced gradients must equal the sum over all 8 views rendered on rank 0 alone."""
+    from manigaussian_b200 import scenes
+    from manigaussian_b200.parallel import shard_views
+    wl = dict(WORKLOADS["c5"])
+    P, W, H, F, VT = wl["P"], wl["W"], wl["H"], wl["F"], 8
+    M = (SH_DEGREE + 1) ** 2
+    g = scenes.make_gaussians(P, F=F, sh_degree=SH_DEGREE, seed=1238)
+    mine = shard_views(VT, rank, world)
+
+    def dev_views(ids):
+        cams = [scenes.make_camera(W, H, v, VT) for v in ids]
+        cts = [scenes.make_cotangents(W, H, F, seed=200 + v) for v in ids]
+        return to_device(g, cams, cts, torch)
+
+    G, C, T = dev_views(mine)
+    flat, acc = make_packed(P, F, M, torch)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        run_step_views(G, C, T, flat, acc, dist, F, False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run_step_views(G, C, T, flat, acc, dist, F, False)
+    e1.record()
+    barrier()
+    tmax = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / steps
+    Rs = [o.num_rendered() for o in G["last_outs"]]
+    out = {"workload": "c5: 1M Gaussians, 8 views 256x256, RGB + 32 features, views sharded v % N, one all-reduce of packed grads",
+           "scaling": "strong", "views_total": VT, "views_per_gpu": [len(shard_views(VT, r, world)) for r in range(world)],
+           "value": P * VT / (ms_step * 1e-3), "unit": "Gaussians/s", "ms_per_step": ms_step, "steps": steps,
+           "allreduce_bytes": int(flat.numel() * 4) if world > 1 else 0,
+           "num_rendered_rank0": Rs}
+    # gradient check of the exchange (rank 0 renders all views alone)
+    if world > 1:
+        run_step_views(G, C, T, flat, acc, dist, F, False)  # one more step: `flat` now holds the all-reduced sum
+        torch.cuda.synchronize()
+        if rank == 0:
+            Ga, Ca, Ta = dev_views(list(range(VT)))
+            flat1, acc1 = make_packed(P, F, M, torch)
+            run_step_views(Ga, Ca, Ta, flat1, acc1, None, F, False)
+            torch.cuda.synchronize()
+            num = float((flat.double() - flat1.double()).norm())
+            den = float(flat1.double().norm())
+            out["grad_check_rel_l2"] = num / den if den > 0 else num
+            out["grad_check"] = "all-reduced gradients of the sharded views vs all 8 views on rank 0 (bar 1e-5, SURVEY.md 8(e))"
+        barrier()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -702,6 +746,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the strong-scaling block (BASELINE configs[4]: 1M Gaussians, 8 views over the ranks)")
     ap.add_argument("--settle", type=float, default=1.5, help="seconds of untimed steps before the W warm-up steps "
                     "(lets clocks/power state and the caching allocator reach steady state)")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the run")
@@ -718,6 +763,11 @@ def main():
            "feature_channels": wl["F"], "depth": wl["depth"], "sh_degree": SH_DEGREE,
            "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of packed per-Gaussian grads per step" if world > 1 else "1 GPU"}
 
+    if world > 1 and rank == 0 and "NCCL_DEBUG" not in os.environ:
+        # record which algorithms/transports NCCL sets up (NVLS = in-switch reduction over NVSwitch) next to the numbers;
+        # must be in the environment before the NCCL library initialises its logging
+        os.environ["MGS_NCCL_LOG"] = f"/tmp/mgs_nccl_{os.getpid()}.log"
+        os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT,ENV,TUNING,NVLS", NCCL_DEBUG_FILE=os.environ["MGS_NCCL_LOG"])
     # ---- CPU-only arm / reference arm without a reference build -------------------------------------------------
     import torch
     use_cpu = a.impl == "cpu"
@@ -740,9 +790,11 @@ def main():
     # ---- GPU arms ------------------------------------------------------------------------------------------------
     torch.cuda.set_device(local_rank)
     dist = None
+    nccl_log = None
     if world > 1:
         import torch.distributed as dist_mod
         import datetime
+        nccl_log = os.environ.get("MGS_NCCL_LOG")
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
         dist = dist_mod
     if wl.get("dyna"):
@@ -755,11 +807,13 @@ def main():
     G, C, T = to_device(g, cams, cts, torch)
     impl = Impl(F, wl["depth"]) if a.impl == "ours" else RefImpl(F, wl["depth"])
     flat, acc = make_packed(P, F, M, torch)
+    packed_bytes = int(flat.numel() * 4)
 
     streams = None
     if a.impl == "ours" and a.streams > 1 and V > 1:
         streams = [torch.cuda.Stream() for _ in range(min(a.streams, V))]
     cfg["view_streams"] = len(streams) if streams else 1
+    meas = {}  # everything MEASURED goes here, `config` only names the workload
 
     def barrier():
         torch.cuda.synchronize()
@@ -779,7 +833,7 @@ def main():
         Rtot = run_step(impl, G, C, T, flat, acc, None, streams)  # no collective: ranks settle for a time, not a count
         torch.cuda.synchronize()
         n_settle += 1
-    cfg["settle_steps"] = n_settle
+    meas["settle_steps"] = n_settle
     for _ in range(a.warmup):
         Rtot = run_step(impl, G, C, T, flat, acc, dist, streams)
     if a.impl == "ours":
@@ -796,10 +850,14 @@ def main():
     barrier()
     t_stop = time.perf_counter()
     hs = sorted((b_ - a_) * 1e3 for a_, b_ in zip([t_start] + step_marks[:-1], step_marks))
-    cfg["host_step_ms"] = {"min": round(hs[0], 3), "median": round(hs[len(hs) // 2], 3), "max": round(hs[-1], 3)}
+    meas["host_step_ms"] = {"min": round(hs[0], 3), "median": round(hs[len(hs) // 2], 3), "max": round(hs[-1], 3)}
+    if G.get("last_outs") is not None and streams and a.impl == "ours":
+        Rtot = sum(o.num_rendered() for o in G["last_outs"])  # read after the timed region: no host sync inside it
+        meas["binning_capacity_per_view"] = [int(o[0]) for o in G["last_outs"]]
+        meas["binning_overflow"] = any(o.overflowed() for o in G["last_outs"])
     clocks = sampler.stop(t_start, t_stop)
     ms = e0.elapsed_time(e1)
-    cfg["wall_ms_per_step"] = (t_stop - t_start) * 1e3 / a.steps
+    meas["wall_ms_per_step"] = (t_stop - t_start) * 1e3 / a.steps
     stages = None
     if a.impl == "ours" and not a.no_stage_timing:
         # per-stage CUDA-event durations for the roofline leg: a separate short pass with views enqueued one after the
@@ -810,6 +868,13 @@ def main():
             run_step(impl, G, C, T, flat, acc, None, None)
         torch.cuda.synchronize()
         stages = _binding.profile_read()
+        if streams:
+            # the timed region's backward runs ONE per-Gaussian kernel for all views after the join: time that launch too
+            run_step(impl, G, C, T, flat, acc, None, streams)
+            torch.cuda.synchronize()
+            mv = _binding.profile_read()
+            if mv.get("project_bwd", (0, 0))[1] > 0:
+                meas["project_bwd_views_ms"] = round(mv["project_bwd"][0] / mv["project_bwd"][1], 4)
         _binding.profile_enable(False)
     tmax = torch.tensor([ms], device="cuda")
     if dist is not None:
@@ -844,6 +909,13 @@ def main():
                        "for all views; reference: its autograd Function per view), and copies the loss to pinned host memory (async, value consumed one "
                        "step later, all K read before the clock stops)"}
 
+    c5 = None
+    if a.impl == "ours" and a.workload == "c3" and not a.no_c5:
+        # drop this workload's device tensors first: the c5 cloud is twice the size
+        del G, C, T, flat, acc
+        torch.cuda.empty_cache()
+        c5 = strong_scaling_c5(torch, dist, rank, world, max(5, a.steps // 4), a.warmup)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -860,19 +932,19 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    out = dict(base, value=value, ms_per_step=ms_step, config=cfg, clocks=clocks)
-    cfg.update(num_rendered_per_view=R_view, R_over_P=R_view / P, alg_bytes_per_view=balg_view,
-               pipeline_hbm_gbs=balg_view * V / (ms_step * 1e-3) / 1e9, pipeline_frac_of_peak=balg_view * V / (ms_step * 1e-3) / 1e9 / peak,
-               l2="no flush: per-step working set (inputs+state+grads, %.0f MB) exceeds the 126 MB L2" % (
-                   (P * (232 + 4 * (27 + F + 3 * M)) + 100 * R_view + 8 * N * (3 + F)) / 1e6))
+    out = dict(base, value=value, ms_per_step=ms_step, config=cfg, measured=meas, clocks=clocks)
+    cfg["l2"] = "no flush: per-step working set (inputs + state + gradients) exceeds the 126 MB L2"
+    meas.update(num_rendered_per_view=R_view, R_over_P=R_view / P, alg_bytes_per_view=balg_view,
+                pipeline_hbm_gbs=balg_view * V / (ms_step * 1e-3) / 1e9, pipeline_frac_of_peak=balg_view * V / (ms_step * 1e-3) / 1e9 / peak,
+                working_set_mb=(P * (232 + 4 * (27 + F + 3 * M)) + 100 * R_view + 8 * N * (3 + F)) / 1e6)
     dom = None
     if stages is not None:
         per = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
-        cfg["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
-        hand = ("project_fwd", "emit_tiles", "ranges_pack", "blend_fwd", "blend_bwd", "project_bwd")
-        # hand-written kernels launched inside the timed region: six per view and step
-        out["gpu_launches"] = len(hand) * V * a.steps
-        cfg["library_launches_cub"] = "depth sort + scan + tile sort (CUB) per view, not counted in gpu_launches"
+        meas["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
+        # hand-written kernels launched inside the timed region, per view and step: project_fwd, emit_tiles, fill_tail,
+        # ranges_pack, blend_fwd, blend_bwd; plus ONE project_bwd_views per step (multi-view path) or one per view
+        out["gpu_launches"] = (6 * V + 1) * a.steps if streams else 6 * V * a.steps
+        meas["library_launches_cub"] = "depth sort + scan + tile sort (CUB) per view, not counted in gpu_launches"
         dom = max(per, key=per.get)
         if per[dom] <= 0:
             dom = None
@@ -890,7 +962,7 @@ def main():
         ach = alg / (per[dom] * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(a.workload, {}).get(dom)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get(a.workload, {}).get(dom)
         except Exception:
             pass
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -899,10 +971,20 @@ def main():
     else:
         if stages is None:
             out["gpu_launches"] = 0
-        out["roofline"] = {"bound": "hbm", "kernel": "whole pipeline", "achieved": cfg["pipeline_hbm_gbs"],
-                           "peak": peak, "unit": "GB/s", "frac": cfg["pipeline_frac_of_peak"], "traffic": None, "peak_source": peak_src}
+        out["roofline"] = {"bound": "hbm", "kernel": "whole pipeline", "achieved": meas["pipeline_hbm_gbs"],
+                           "peak": peak, "unit": "GB/s", "frac": meas["pipeline_frac_of_peak"], "traffic": None, "peak_source": peak_src}
     if e2e is not None:
         out["e2e"] = e2e
+    if c5 is not None:
+        out["c5"] = c5
+    if nccl_log and os.path.exists(nccl_log):
+        try:
+            lines = [ln.strip() for ln in open(nccl_log, errors="replace") if any(k in ln for k in ("NVLS", "NCCL version", "Using network", "Channel", "nRanks", "P2P", "Ring", "Tree", "TUNING"))]
+            keep = [ln for ln in lines if "Channel " not in ln and "via P2P" not in ln][:12]
+            out["nccl"] = {"log_lines": [ln[-200:] for ln in keep], "nvls_lines": sum("NVLS" in ln for ln in lines),
+                           "allreduce_bytes_per_step": packed_bytes}
+        except Exception as ex:  # pragma: no cover
+            out["nccl"] = {"error": str(ex)}
     if a.gpus == 1 and not a.no_cpu_baseline:
         try:
             out["cpu_baseline"] = cpu_baseline(wl)[0]

@@ -150,9 +150,9 @@ int mgs_forward_finish(
  *     dL_dscale [P,3], dL_drot [P,4].
  *   blend_scratch: device scratch of mgs_backward_scratch_bytes(P) bytes (contents irrelevant on entry).
  *   accumulate: 0 = every output row is written exactly once (the reference's semantics after its zero-fill);
- *               1 = every output is ADDED into the caller's buffer with L2 reductions (red.global.add), so several
- *                   views, possibly on different streams, can sum straight into one packed gradient buffer -- the
- *                   message of the multi-GPU all-reduce -- without intermediate tensors (no reference counterpart).
+ *               1 = every output row is ADDED to what the caller's buffer holds (read-modify-write by the row's one
+ *                   thread; dL_dfeature with L2 reductions).  Calls that share output buffers must be serialised by
+ *                   the caller; for several views of one cloud use mgs_backward_views, which sums in registers.
  */
 size_t mgs_backward_scratch_bytes(int P);
 int mgs_backward(
@@ -192,6 +192,87 @@ int mgs_backward(
 	int accumulate,
 	int debug,
 	void* stream);
+
+/*
+ * Multi-view step (no reference counterpart: the reference renders one view per call, asserts batch size 1 in its
+ * caller, agents/manigaussian_bc/neural_rendering.py:386, and blocks the host on every view's instance count,
+ * rasterizer_impl.cu:284).  V views of ONE Gaussian cloud are enqueued by ONE call with NO host synchronisation:
+ * the caller owns the three state buffers of every view and sizes the binning state for `binning_capacity` instances
+ * (mgs_binning_state_bytes(capacity)) -- e.g. the previous step's count plus slack; the real count stays on the device.
+ * If it exceeds the capacity, the instances beyond it (the farthest Gaussians: emission is in depth order) are dropped,
+ * the image is still well defined and consistent with the backward, and status[1] is raised; status (2 ints, pinned host
+ * memory recommended, may be NULL) receives {instance count, overflow flag} asynchronously on the view's stream.
+ * Work of view v is enqueued on views[v].stream; every view stream first waits for what `join_stream` holds at the call,
+ * and `join_stream` waits for every view stream before the call returns, so the caller needs no stream logic of its own
+ * (a view whose stream IS join_stream is simply serialised).  Nothing in these calls allocates or blocks: a step built
+ * from them can be captured in a CUDA graph.
+ * mgs_backward_views runs the blend backward of every view on its stream, joins, and runs ONE per-Gaussian chain-rule
+ * kernel that sums over the views in registers: outputs are the SUMS over the V views (the packed buffer of the
+ * multi-GPU all-reduce can be passed directly), except dL_dmean2D which each view owns ([P,3], shared_mean2D = 0) or
+ * which is summed into views[0].dL_dmean2D (shared_mean2D = 1).  Output NULL-ability as in mgs_backward.
+ */
+typedef struct mgs_view {
+	const float* viewmatrix;     /* device, 16 floats */
+	const float* projmatrix;     /* device, 16 floats */
+	const float* cam_pos;        /* device, 3 floats (NULL with precomputed colours) */
+	const float* background;     /* device, 3 floats */
+	float tan_fovx, tan_fovy;
+	int width, height;
+	char* geometry_state;        /* mgs_geometry_state_bytes(P) */
+	char* binning_state;         /* mgs_binning_state_bytes(binning_capacity) */
+	char* image_state;           /* mgs_image_state_bytes(width, height) */
+	int binning_capacity;
+	float* out_color;            /* forward outputs: [3,H,W], [F,H,W] or NULL, [H,W] or NULL, int32 [P] */
+	float* out_feature;
+	float* out_depth;
+	int* radii;
+	int* status;                 /* host-accessible, 2 ints, or NULL */
+	const float* dL_dpix;        /* backward inputs: [3,H,W], [F,H,W] or NULL, [H,W] or NULL */
+	const float* dL_dpix_F;
+	const float* dL_dpix_depth;
+	char* blend_scratch;         /* backward: mgs_backward_scratch_bytes(P) */
+	float* dL_dmean2D;           /* backward output [P,3] or NULL */
+	void* stream;
+} mgs_view;
+
+int mgs_forward_views(
+	int V, const mgs_view* views,
+	int P, int D, int M, int F,
+	const float* means3D,
+	const float* shs,
+	const float* colors_precomp,
+	const float* feature_precomp,
+	const float* opacities,
+	const float* scales,
+	float scale_modifier,
+	const float* rotations,
+	const float* cov3D_precomp,
+	int prefiltered,
+	int debug,
+	void* join_stream);
+int mgs_backward_views(
+	int V, const mgs_view* views,
+	int P, int D, int M, int F,
+	const float* means3D,
+	const float* shs,
+	const float* colors_precomp,
+	const float* feature_precomp,
+	const float* scales,
+	float scale_modifier,
+	const float* rotations,
+	const float* cov3D_precomp,
+	float* dL_dmean3D,
+	float* dL_dopacity,
+	float* dL_dcolor,
+	float* dL_dfeature,
+	float* dL_dcov3D,
+	float* dL_dsh,
+	float* dL_dscale,
+	float* dL_drot,
+	int shared_mean2D,
+	int accumulate,
+	int debug,
+	void* join_stream);
 
 /* Frustum test.  Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
  * present: uint8 [P], 1 where view-space z > 0.2. */

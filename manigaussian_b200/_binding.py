@@ -11,6 +11,20 @@ from . import build as _build
 _c_float_p = C.c_void_p  # device pointers are passed as integers
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
+
+
+class View(C.Structure):
+    """mirror of `mgs_view` (include/mgs_rasterizer.h)"""
+    _fields_ = [("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("cam_pos", C.c_void_p), ("background", C.c_void_p),
+                ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("width", C.c_int), ("height", C.c_int),
+                ("geometry_state", C.c_void_p), ("binning_state", C.c_void_p), ("image_state", C.c_void_p),
+                ("binning_capacity", C.c_int),
+                ("out_color", C.c_void_p), ("out_feature", C.c_void_p), ("out_depth", C.c_void_p), ("radii", C.c_void_p),
+                ("status", C.c_void_p),
+                ("dL_dpix", C.c_void_p), ("dL_dpix_F", C.c_void_p), ("dL_dpix_depth", C.c_void_p),
+                ("blend_scratch", C.c_void_p), ("dL_dmean2D", C.c_void_p), ("stream", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -56,6 +70,17 @@ def lib():
                                vp, vp, vp, vp, vp,   # dL_dmean2D dL_dconic dL_dopacity dL_dcolor dL_dfeature
                                vp, vp, vp, vp, vp,   # dL_dmean3D dL_dcov3D dL_dsh dL_dscale dL_drot
                                vp, i, i, vp]         # scratch accumulate debug stream
+    L.mgs_forward_views.restype = C.c_int
+    L.mgs_forward_views.argtypes = [i, C.POINTER(View), i, i, i, i,     # V views P D M F
+                                    vp, vp, vp, vp,                     # means3D shs colors feature
+                                    vp, vp, f, vp, vp,                  # opacities scales scale_modifier rotations cov3D_precomp
+                                    i, i, vp]                           # prefiltered debug join_stream
+    L.mgs_backward_views.restype = C.c_int
+    L.mgs_backward_views.argtypes = [i, C.POINTER(View), i, i, i, i,    # V views P D M F
+                                     vp, vp, vp, vp,                    # means3D shs colors feature
+                                     vp, f, vp, vp,                     # scales scale_modifier rotations cov3D_precomp
+                                     vp, vp, vp, vp, vp, vp, vp, vp,    # dL: mean3D opacity color feature cov3D sh scale rot
+                                     i, i, i, vp]                       # shared_mean2D accumulate debug join_stream
     L.mgs_mark_visible.restype = C.c_int
     L.mgs_mark_visible.argtypes = [i, vp, vp, vp, vp, vp]
     L.mgs_state_array.restype = C.c_int
@@ -74,7 +99,7 @@ def lib():
                                         vp, vp, vp, vp, vp,             # g_means g_rot g_scales g_opac g_feature
                                         vp, vp, vp, vp, vp, vp, vp, vp, # dL: means d_means rot d_rot scales d_scales opac feature
                                         vp]
-    if L.mgs_abi_version() != 102:
+    if L.mgs_abi_version() != 200:
         raise ImportError("manigaussian_b200: ABI version mismatch")
     _lib = L
     return L
@@ -83,7 +108,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "mgs_abi_version", "mgs_last_error", "mgs_geometry_state_bytes", "mgs_image_state_bytes",
     "mgs_binning_state_bytes", "mgs_backward_scratch_bytes", "mgs_forward", "mgs_forward_begin", "mgs_forward_finish",
-    "mgs_backward",
+    "mgs_backward", "mgs_forward_views", "mgs_backward_views",
     "mgs_activate", "mgs_activate_backward",
     "mgs_mark_visible", "mgs_state_array", "mgs_profile_enable", "mgs_profile_num_stages",
     "mgs_profile_stage_name", "mgs_profile_read",

@@ -115,13 +115,14 @@ struct GeomState {
 	}
 };
 struct ImageState {
-	float* final_T; uint32_t* n_contrib; uint2* ranges;
+	float* final_T; uint32_t* n_contrib; uint2* ranges; int* status;
 	static ImageState carve(char*& chunk, size_t N, size_t T)
 	{
 		ImageState s;
 		obtain(chunk, s.final_T, N);
 		obtain(chunk, s.n_contrib, N);
 		obtain(chunk, s.ranges, T);
+		obtain(chunk, s.status, 4);  // {instance count, overflow flag} of a forward that did not read the count back
 		return s;
 	}
 };
@@ -166,7 +167,7 @@ using namespace mgs;
 
 extern "C" {
 
-int mgs_abi_version(void) { return 102; }
+int mgs_abi_version(void) { return 200; }
 const char* mgs_last_error(void) { return g_err.c_str(); }
 
 size_t mgs_geometry_state_bytes(int P) { return required([&](char*& p) { GeomState::carve(p, (size_t)P); }); }
@@ -254,7 +255,8 @@ static int forward_phase2(
 	if (stages & 1) {
 	{
 		StageTimer t_(ST_EMIT, st);
-		launch_emit_tiles(P, geom.order, geom.means2D, geom.point_offsets, radii, gx, gy, bin.tile_keys_unsorted, bin.point_list_unsorted, st);
+		launch_emit_tiles(P, geom.order, geom.means2D, geom.point_offsets, radii, gx, gy, bin.tile_keys_unsorted, bin.point_list_unsorted,
+			(uint32_t)num_rendered, nullptr, st);
 	}
 	MGS_STAGE("emit_tiles");
 	if (num_rendered > 0) {
@@ -267,8 +269,8 @@ static int forward_phase2(
 	}
 	{
 		StageTimer t_(ST_RANGES_PACK, st);
-		launch_ranges_and_pack(num_rendered, (int)T, gx, bin.tile_keys, bin.point_list, geom.means2D, geom.conic_opacity, geom.extent,
-			img.ranges, bin.recs, st);
+		launch_ranges_and_pack(num_rendered, nullptr, num_rendered, (int)T, gx, bin.tile_keys, bin.point_list, geom.means2D, geom.conic_opacity,
+			geom.extent, img.ranges, bin.recs, st);
 	}
 	MGS_STAGE("ranges_pack");
 	}
@@ -411,21 +413,272 @@ int mgs_backward(
 		MGS_STAGE("blend_bwd");
 	}
 
-	ProjectBwdArgs pb{};
-	pb.P = P; pb.D = D; pb.M = M;
-	pb.means3D = means3D; pb.radii = radii; pb.shs = shs; pb.clamped = geom.clamped;
-	pb.scales = scales; pb.rotations = rotations; pb.scale_modifier = scale_modifier;
-	pb.cov3D = geom.cov3D; pb.cov3D_precomp = cov3D_precomp;
-	pb.viewmatrix = viewmatrix; pb.projmatrix = projmatrix; pb.cam_pos = campos;
-	pb.tan_fovx = tan_fovx; pb.tan_fovy = tan_fovy; pb.focal_x = focal_x; pb.focal_y = focal_y;
-	pb.gb = gb; pb.accumulate = accumulate;
-	pb.dL_dmean2D = dL_dmean2D; pb.dL_dconic = dL_dconic; pb.dL_dopacity = dL_dopacity; pb.dL_dcolor = dL_dcolor;
-	pb.dL_dmean3D = dL_dmean3D; pb.dL_dcov3D = dL_dcov3D; pb.dL_dsh = shs ? dL_dsh : nullptr;
-	pb.dL_dscale = dL_dscale; pb.dL_drot = dL_drot; pb.dL_ddepth = nullptr;
-	if (shs && !dL_dsh) pb.shs = nullptr;
-	if (!scales || !rotations || !dL_dscale || !dL_drot) { pb.scales = nullptr; }
-	{ StageTimer t_(ST_PROJECT_BWD, st); launch_project_bwd(pb, st); }
+	ProjectBwdViewsArgs pb{};
+	pb.P = P; pb.D = D; pb.M = M; pb.V = 1;
+	pb.means3D = means3D; pb.shs = (shs && dL_dsh) ? shs : nullptr;
+	const bool have_sr = scales && rotations && dL_dscale && dL_drot;
+	pb.scales = have_sr ? scales : nullptr; pb.rotations = rotations; pb.scale_modifier = scale_modifier;
+	pb.cov3D_precomp = cov3D_precomp ? cov3D_precomp : geom.cov3D;
+	if (!have_sr && !pb.cov3D_precomp) return fail(MGS_ERR_INVALID_ARG, "provide scales+rotations or a precomputed 3D covariance");
+	pb.accumulate = accumulate; pb.shared_mean2D = 1;
+	pb.dL_dmean3D = dL_dmean3D; pb.dL_dopacity = dL_dopacity; pb.dL_dcolor = dL_dcolor; pb.dL_dcov3D = dL_dcov3D;
+	pb.dL_dsh = pb.shs ? dL_dsh : nullptr; pb.dL_dscale = have_sr ? dL_dscale : nullptr; pb.dL_drot = have_sr ? dL_drot : nullptr;
+	pb.dL_dconic = accumulate ? nullptr : dL_dconic;
+	ProjectBwdView& pv = pb.view[0];
+	pv.radii = radii; pv.gb = gb; pv.clamped = geom.clamped; pv.viewmatrix = viewmatrix; pv.projmatrix = projmatrix; pv.cam_pos = campos;
+	pv.dL_dmean2D = dL_dmean2D; pv.tan_fovx = tan_fovx; pv.tan_fovy = tan_fovy; pv.focal_x = focal_x; pv.focal_y = focal_y;
+	{ StageTimer t_(ST_PROJECT_BWD, st); launch_project_bwd_views(pb, st); }
 	MGS_STAGE("project_bwd");
+	return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Multi-view step entry points: V views of ONE Gaussian cloud, no host synchronisation anywhere.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace mgs {
+// fork/join events between the caller's stream and the per-view streams (created once, reused; never destroyed)
+struct EventPool {
+	std::mutex mu;
+	std::vector<cudaEvent_t> free_;
+	cudaEvent_t get()
+	{
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			if (!free_.empty()) { cudaEvent_t e = free_.back(); free_.pop_back(); return e; }
+		}
+		cudaEvent_t e = nullptr;
+		cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+		return e;
+	}
+	void put(cudaEvent_t e) { std::lock_guard<std::mutex> lk(mu); free_.push_back(e); }
+};
+static EventPool g_events;
+
+// every view stream waits for what the join stream has enqueued so far
+static int fork_streams(int V, const mgs_view* views, cudaStream_t join)
+{
+	bool need = false;
+	for (int v = 0; v < V; v++) need |= reinterpret_cast<cudaStream_t>(views[v].stream) != join;
+	if (!need) return 0;
+	cudaEvent_t e = g_events.get();
+	MGS_CUDA(cudaEventRecord(e, join));
+	for (int v = 0; v < V; v++) {
+		cudaStream_t st = reinterpret_cast<cudaStream_t>(views[v].stream);
+		if (st != join) MGS_CUDA(cudaStreamWaitEvent(st, e, 0));
+	}
+	g_events.put(e);  // recorded and waited on: safe to re-record later (waits captured the earlier record)
+	return 0;
+}
+// the join stream waits for every view stream
+static int join_streams(int V, const mgs_view* views, cudaStream_t join)
+{
+	for (int v = 0; v < V; v++) {
+		cudaStream_t st = reinterpret_cast<cudaStream_t>(views[v].stream);
+		if (st == join) continue;
+		bool seen = false;
+		for (int u = 0; u < v; u++) seen |= views[u].stream == views[v].stream;
+		if (seen) continue;
+		cudaEvent_t e = g_events.get();
+		MGS_CUDA(cudaEventRecord(e, st));
+		MGS_CUDA(cudaStreamWaitEvent(join, e, 0));
+		g_events.put(e);
+	}
+	return 0;
+}
+}  // namespace mgs
+
+int mgs_forward_views(
+	int V, const mgs_view* views,
+	int P, int D, int M, int F,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* feature_precomp,
+	const float* opacities, const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	int prefiltered, int debug, void* join_stream)
+{
+	(void)prefiltered;
+	if (V <= 0 || !views) return fail(MGS_ERR_INVALID_ARG, "need at least one view");
+	if (P <= 0) return fail(MGS_ERR_INVALID_ARG, "P must be > 0");
+	if (!means3D || !opacities) return fail(MGS_ERR_INVALID_ARG, "means3D/opacities are required");
+	if (!colors_precomp && !shs) return fail(MGS_ERR_INVALID_ARG, "provide SHs or precomputed colours");
+	if (!cov3D_precomp && (!scales || !rotations)) return fail(MGS_ERR_INVALID_ARG, "provide scales+rotations or a precomputed 3D covariance");
+	if (F < 0 || F > MGS_MAX_FEATURE_CHANNELS || !blend_supported(F)) return fail(MGS_ERR_UNSUPPORTED, "feature channel count must be in [0, 32]");
+	for (int v = 0; v < V; v++) {
+		const mgs_view& w = views[v];
+		if (!w.viewmatrix || !w.projmatrix || !w.background || !w.geometry_state || !w.binning_state || !w.image_state || !w.out_color || !w.radii)
+			return fail(MGS_ERR_INVALID_ARG, "view: matrices, background, the three state buffers, out_color and radii are required");
+		if (!colors_precomp && !w.cam_pos) return fail(MGS_ERR_INVALID_ARG, "view: cam_pos is required with SHs");
+		if (w.width <= 0 || w.height <= 0 || w.binning_capacity < 0) return fail(MGS_ERR_INVALID_ARG, "view: bad size or capacity");
+	}
+	cudaStream_t join = reinterpret_cast<cudaStream_t>(join_stream);
+	int rc = fork_streams(V, views, join);
+	if (rc < 0) return rc;
+	// stage by stage across the views: the short per-Gaussian and binning kernels of every view are enqueued before any
+	// view's long blend kernel, so no view's chain queues behind another view's blend
+	for (int phase = 0; phase < 3; phase++) {
+		for (int v = 0; v < V; v++) {
+			const mgs_view& w = views[v];
+			cudaStream_t st = reinterpret_cast<cudaStream_t>(w.stream);
+			const int gx = ceil_div(w.width, TILE_X), gy = ceil_div(w.height, TILE_Y);
+			const size_t N = (size_t)w.width * w.height, T = (size_t)gx * gy;
+			char* gchunk = w.geometry_state; char* ichunk = w.image_state; char* bchunk = w.binning_state;
+			GeomState geom = GeomState::carve(gchunk, (size_t)P);
+			ImageState img = ImageState::carve(ichunk, N, T);
+			BinState bin = BinState::carve(bchunk, (size_t)w.binning_capacity);
+			const int Fv = (F > 0 && feature_precomp && w.out_feature) ? F : 0;
+			if (phase == 0) {
+				ProjectFwdArgs pa{};
+				pa.P = P; pa.D = D; pa.M = M;
+				pa.means3D = means3D; pa.scales = scales; pa.scale_modifier = scale_modifier; pa.rotations = rotations;
+				pa.opacities = opacities; pa.shs = shs; pa.cov3D_precomp = cov3D_precomp; pa.colors_precomp = colors_precomp;
+				pa.viewmatrix = w.viewmatrix; pa.projmatrix = w.projmatrix; pa.cam_pos = w.cam_pos;
+				pa.W = w.width; pa.H = w.height; pa.tan_fovx = w.tan_fovx; pa.tan_fovy = w.tan_fovy;
+				pa.focal_x = w.width / (2.0f * w.tan_fovx); pa.focal_y = w.height / (2.0f * w.tan_fovy);
+				pa.grid_x = gx; pa.grid_y = gy;
+				pa.radii = w.radii; pa.means2D = geom.means2D; pa.depths = geom.depths; pa.cov3D = geom.cov3D; pa.rgbd = geom.rgbd;
+				pa.conic_opacity = geom.conic_opacity; pa.extent = geom.extent; pa.clamped = geom.clamped; pa.tiles_touched = geom.tiles_touched;
+				pa.iota = geom.iota;
+				{ StageTimer t_(ST_PROJECT_FWD, st); launch_project_fwd(pa, st); }
+				MGS_STAGE("project_fwd");
+				{
+					StageTimer t_(ST_DEPTH_SORT, st);
+					launch_depth_sort(geom.temp, geom.temp_bytes, reinterpret_cast<const uint32_t*>(geom.depths), geom.depth_sorted, geom.iota,
+						geom.order, P, st);
+				}
+				MGS_STAGE("depth_sort");
+				{ StageTimer t_(ST_SCAN, st); launch_scan_sorted(geom.temp, geom.temp_bytes, geom.order, geom.tiles_touched, geom.point_offsets, P, st); }
+				MGS_STAGE("scan");
+			} else if (phase == 1) {
+				const uint32_t cap = (uint32_t)w.binning_capacity;
+				{
+					StageTimer t_(ST_EMIT, st);
+					launch_emit_tiles(P, geom.order, geom.means2D, geom.point_offsets, w.radii, gx, gy, bin.tile_keys_unsorted, bin.point_list_unsorted,
+						cap, img.status, st);
+					// the slots behind the R real instances sort to the very end: last tile id, ids never read
+					launch_fill_tail(geom.point_offsets, P, cap, (uint32_t)(T - 1), bin.tile_keys_unsorted, bin.point_list_unsorted, st);
+				}
+				MGS_STAGE("emit_tiles");
+				if (cap > 0) {
+					const int bit = T > 1 ? higher_msb((uint32_t)(T - 1)) : 1;
+					StageTimer t_(ST_SORT, st);
+					launch_tile_sort(bin.sort_temp, bin.sort_bytes, bin.tile_keys_unsorted, bin.tile_keys, bin.point_list_unsorted, bin.point_list,
+						(int)cap, bit, st);
+					MGS_STAGE("tile_sort");
+				}
+				{
+					StageTimer t_(ST_RANGES_PACK, st);
+					launch_ranges_and_pack(-1, geom.point_offsets + P - 1, (int)cap, (int)T, gx, bin.tile_keys, bin.point_list, geom.means2D,
+						geom.conic_opacity, geom.extent, img.ranges, bin.recs, st);
+				}
+				MGS_STAGE("ranges_pack");
+				if (w.status) MGS_CUDA(cudaMemcpyAsync(w.status, img.status, 2 * sizeof(int), cudaMemcpyDefault, st));
+			} else {
+				BlendArgs ba{};
+				ba.W = w.width; ba.H = w.height; ba.grid_x = gx; ba.grid_y = gy; ba.F = Fv;
+				ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
+				ba.rgbd = geom.rgbd; ba.feature = Fv > 0 ? feature_precomp : nullptr; ba.bg = w.background;
+				ba.want_depth = w.out_depth != nullptr;
+				ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
+				ba.out_color = w.out_color; ba.out_feature = w.out_feature; ba.out_depth = w.out_depth;
+				{ StageTimer t_(ST_BLEND_FWD, st); launch_blend_fwd(ba, st); }
+				MGS_STAGE("blend_fwd");
+			}
+		}
+	}
+	return join_streams(V, views, join);
+}
+
+int mgs_backward_views(
+	int V, const mgs_view* views,
+	int P, int D, int M, int F,
+	const float* means3D, const float* shs, const float* colors_precomp, const float* feature_precomp,
+	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+	float* dL_dmean3D, float* dL_dopacity, float* dL_dcolor, float* dL_dfeature, float* dL_dcov3D, float* dL_dsh,
+	float* dL_dscale, float* dL_drot, int shared_mean2D, int accumulate, int debug, void* join_stream)
+{
+	(void)colors_precomp;
+	if (V <= 0 || !views) return fail(MGS_ERR_INVALID_ARG, "need at least one view");
+	if (P <= 0) return fail(MGS_ERR_INVALID_ARG, "P must be > 0");
+	if (!means3D || !dL_dmean3D || !dL_dopacity) return fail(MGS_ERR_INVALID_ARG, "means3D, dL_dmean3D and dL_dopacity are required");
+	if (F < 0 || F > MGS_MAX_FEATURE_CHANNELS) return fail(MGS_ERR_UNSUPPORTED, "feature channel count must be in [0, 32]");
+	if (F > 0 && (!feature_precomp || !dL_dfeature)) F = 0;
+	for (int v = 0; v < V; v++) {
+		const mgs_view& w = views[v];
+		if (!w.viewmatrix || !w.projmatrix || !w.background || !w.geometry_state || !w.binning_state || !w.image_state || !w.radii ||
+			!w.dL_dpix || !w.blend_scratch)
+			return fail(MGS_ERR_INVALID_ARG, "view: matrices, background, state buffers, radii, dL_dpix and blend_scratch are required");
+		if (F > 0 && !w.dL_dpix_F) return fail(MGS_ERR_INVALID_ARG, "view: dL_dpix_F is required with features");
+	}
+	cudaStream_t join = reinterpret_cast<cudaStream_t>(join_stream);
+	{
+		cudaStream_t st = join;  // for MGS_CUDA's messages
+		(void)st;
+		if (F > 0 && !accumulate) MGS_CUDA(cudaMemsetAsync(dL_dfeature, 0, (size_t)P * F * sizeof(float), join));
+	}
+	int rc = fork_streams(V, views, join);
+	if (rc < 0) return rc;
+	// blend stage of every view on its own stream: per-view blend-stage records, feature gradients summed with 128-bit
+	// reductions straight into dL_dfeature
+	for (int v = 0; v < V; v++) {
+		const mgs_view& w = views[v];
+		cudaStream_t st = reinterpret_cast<cudaStream_t>(w.stream);
+		const int gx = ceil_div(w.width, TILE_X), gy = ceil_div(w.height, TILE_Y);
+		const size_t N = (size_t)w.width * w.height, T = (size_t)gx * gy;
+		char* gchunk = w.geometry_state; char* ichunk = w.image_state; char* bchunk = w.binning_state; char* schunk = w.blend_scratch;
+		GeomState geom = GeomState::carve(gchunk, (size_t)P);
+		ImageState img = ImageState::carve(ichunk, N, T);
+		BinState bin = BinState::carve(bchunk, (size_t)w.binning_capacity);
+		float* gb = nullptr;
+		obtain(schunk, gb, (size_t)P * GB_STRIDE);
+		MGS_CUDA(cudaMemsetAsync(gb, 0, (size_t)P * GB_STRIDE * sizeof(float), st));
+		BlendArgs ba{};
+		ba.W = w.width; ba.H = w.height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F;
+		ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
+		ba.rgbd = geom.rgbd; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = w.background;
+		ba.want_depth = w.dL_dpix_depth != nullptr;
+		ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
+		ba.dL_dcolor = w.dL_dpix; ba.dL_dfeature = F > 0 ? w.dL_dpix_F : nullptr; ba.dL_ddepth = w.dL_dpix_depth;
+		ba.gb = gb; ba.dL_dfeat = F > 0 ? dL_dfeature : nullptr;
+		if (w.binning_capacity > 0) {
+			{ StageTimer t_(ST_BLEND_BWD, st); launch_blend_bwd(ba, st); }
+			MGS_STAGE("blend_bwd");
+		}
+	}
+	rc = join_streams(V, views, join);
+	if (rc < 0) return rc;
+	// one launch per MAX_BWD_VIEWS views: the per-Gaussian chain rule, summed over the views in registers
+	const bool have_sr = scales && rotations && dL_dscale && dL_drot;
+	for (int v0 = 0; v0 < V; v0 += MAX_BWD_VIEWS) {
+		cudaStream_t st = join;
+		ProjectBwdViewsArgs pb{};
+		pb.P = P; pb.D = D; pb.M = M; pb.V = std::min(V - v0, (int)MAX_BWD_VIEWS);
+		pb.means3D = means3D; pb.shs = (shs && dL_dsh) ? shs : nullptr;
+		pb.scales = have_sr ? scales : nullptr; pb.rotations = rotations; pb.scale_modifier = scale_modifier;
+		pb.cov3D_precomp = cov3D_precomp;
+		if (!have_sr && !cov3D_precomp) {
+			// gradients w.r.t. scale/rotation not requested: the forward's own covariance (any view's copy) serves
+			char* gchunk = views[0].geometry_state;
+			pb.cov3D_precomp = GeomState::carve(gchunk, (size_t)P).cov3D;
+		}
+		pb.accumulate = (accumulate || v0 > 0) ? 1 : 0;
+		pb.shared_mean2D = shared_mean2D;
+		pb.dL_dmean3D = dL_dmean3D; pb.dL_dopacity = dL_dopacity; pb.dL_dcolor = dL_dcolor; pb.dL_dcov3D = dL_dcov3D;
+		pb.dL_dsh = pb.shs ? dL_dsh : nullptr; pb.dL_dscale = have_sr ? dL_dscale : nullptr; pb.dL_drot = have_sr ? dL_drot : nullptr;
+		pb.dL_dconic = nullptr;
+		for (int u = 0; u < pb.V; u++) {
+			const mgs_view& w = views[v0 + u];
+			char* gchunk = w.geometry_state; char* schunk = w.blend_scratch;
+			GeomState geom = GeomState::carve(gchunk, (size_t)P);
+			float* gb = nullptr;
+			obtain(schunk, gb, (size_t)P * GB_STRIDE);
+			ProjectBwdView& pv = pb.view[u];
+			pv.radii = w.radii; pv.gb = gb; pv.clamped = geom.clamped; pv.viewmatrix = w.viewmatrix; pv.projmatrix = w.projmatrix;
+			pv.cam_pos = w.cam_pos; pv.dL_dmean2D = shared_mean2D ? views[0].dL_dmean2D : w.dL_dmean2D;
+			pv.tan_fovx = w.tan_fovx; pv.tan_fovy = w.tan_fovy;
+			pv.focal_x = w.width / (2.0f * w.tan_fovx); pv.focal_y = w.height / (2.0f * w.tan_fovy);
+		}
+		{ StageTimer t_(ST_PROJECT_BWD, st); launch_project_bwd_views(pb, st); }
+		MGS_STAGE("project_bwd");
+	}
 	return 0;
 }
 

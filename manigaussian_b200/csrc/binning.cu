@@ -68,13 +68,21 @@ void launch_scan_sorted(void* temp, size_t temp_bytes, const uint32_t* order, co
 	cub::DeviceScan::InclusiveSum(temp, temp_bytes, it, offsets, P, s);
 }
 
-// One thread per Gaussian in depth order; emits its tile rect row-major (y outer, x inner).
+// One thread per Gaussian in depth order; emits its tile rect row-major (y outer, x inner).  The instance arrays hold
+// `capacity` slots: when the caller sized them without knowing the instance count (no host read-back), instances
+// beyond the capacity -- the farthest Gaussians, emission is in depth order -- are dropped and status[1] is raised.
 __global__ void __launch_bounds__(256) emit_tiles_kernel(int P, const uint32_t* __restrict__ order,
 	const float2* __restrict__ means2D, const uint32_t* __restrict__ offsets, const int* __restrict__ radii,
-	uint32_t grid_x, uint32_t grid_y, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ values)
+	uint32_t grid_x, uint32_t grid_y, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ values, uint32_t capacity,
+	int* __restrict__ status)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= P) return;
+	if (i == P - 1 && status) {
+		const uint32_t R = offsets[P - 1];
+		status[0] = (int)R;
+		status[1] = R > capacity ? 1 : 0;
+	}
 	const uint32_t g = order[i];
 	const int radius = radii[g];
 	if (radius <= 0) return;
@@ -84,17 +92,33 @@ __global__ void __launch_bounds__(256) emit_tiles_kernel(int P, const uint32_t* 
 	tile_rect(xy.x, xy.y, radius, rmin, rmax, grid_x, grid_y);
 	for (uint32_t y = rmin.y; y < rmax.y; y++) {
 		for (uint32_t x = rmin.x; x < rmax.x; x++) {
-			tile_keys[off] = y * grid_x + x;
-			values[off] = g;
+			if (off < capacity) {
+				tile_keys[off] = y * grid_x + x;
+				values[off] = g;
+			}
 			off++;
 		}
 	}
 }
 
 void launch_emit_tiles(int P, const uint32_t* order, const float2* means2D, const uint32_t* offsets, const int* radii,
-	uint32_t grid_x, uint32_t grid_y, uint32_t* tile_keys, uint32_t* values, cudaStream_t s)
+	uint32_t grid_x, uint32_t grid_y, uint32_t* tile_keys, uint32_t* values, uint32_t capacity, int* status, cudaStream_t s)
 {
-	if (P > 0) emit_tiles_kernel<<<ceil_div(P, 256), 256, 0, s>>>(P, order, means2D, offsets, radii, grid_x, grid_y, tile_keys, values);
+	if (P > 0) emit_tiles_kernel<<<ceil_div(P, 256), 256, 0, s>>>(P, order, means2D, offsets, radii, grid_x, grid_y, tile_keys, values, capacity, status);
+}
+
+__global__ void __launch_bounds__(256) fill_tail_kernel(const uint32_t* __restrict__ offsets, int P, uint32_t capacity, uint32_t last_tile,
+	uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ values)
+{
+	const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= capacity || idx < offsets[P - 1]) return;
+	tile_keys[idx] = last_tile;
+	values[idx] = 0xffffffffu;
+}
+
+void launch_fill_tail(const uint32_t* offsets, int P, uint32_t capacity, uint32_t last_tile, uint32_t* tile_keys, uint32_t* values, cudaStream_t s)
+{
+	if (capacity > 0) fill_tail_kernel<<<ceil_div((int)capacity, 256), 256, 0, s>>>(offsets, P, capacity, last_tile, tile_keys, values);
 }
 
 void launch_tile_sort(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
@@ -142,12 +166,14 @@ __device__ __forceinline__ uint32_t block_mask(float gx, float gy, float ca, flo
 }
 
 // One thread per sorted instance: tile boundary detection + gather of the 32-byte blend record.
-__global__ void __launch_bounds__(256) ranges_pack_kernel(int R, int grid_x, const uint32_t* __restrict__ tile_keys,
+__global__ void __launch_bounds__(256) ranges_pack_kernel(int R_host, const uint32_t* __restrict__ R_dev, int capacity, int grid_x,
+	const uint32_t* __restrict__ tile_keys,
 	const uint32_t* __restrict__ point_list, const float2* __restrict__ means2D,
 	const float4* __restrict__ conic_opacity, const float2* __restrict__ extent,
 	uint2* __restrict__ ranges, InstRec* __restrict__ recs)
 {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const int R = R_host >= 0 ? R_host : (int)min(*R_dev, (uint32_t)capacity);
 	if (idx >= R) return;
 	const uint32_t currtile = tile_keys[idx];
 	if (idx == 0) {
@@ -171,11 +197,13 @@ __global__ void __launch_bounds__(256) ranges_pack_kernel(int R, int grid_x, con
 	dst[1] = make_float4(co.z, co.w, __uint_as_float(mask), __uint_as_float(g));
 }
 
-void launch_ranges_and_pack(int R, int num_tiles, int grid_x, const uint32_t* tile_keys, const uint32_t* point_list,
-	const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs, cudaStream_t s)
+void launch_ranges_and_pack(int R, const uint32_t* R_dev, int capacity, int num_tiles, int grid_x, const uint32_t* tile_keys,
+	const uint32_t* point_list, const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs,
+	cudaStream_t s)
 {
 	cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s);
-	if (R > 0) ranges_pack_kernel<<<ceil_div(R, 256), 256, 0, s>>>(R, grid_x, tile_keys, point_list, means2D, conic_opacity, extent, ranges, recs);
+	const int n = R >= 0 ? R : capacity;
+	if (n > 0) ranges_pack_kernel<<<ceil_div(n, 256), 256, 0, s>>>(R, R_dev, capacity, grid_x, tile_keys, point_list, means2D, conic_opacity, extent, ranges, recs);
 }
 
 }  // namespace mgs

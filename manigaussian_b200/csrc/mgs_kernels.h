@@ -37,34 +37,37 @@ struct ProjectFwdArgs {
 	uint32_t* iota;    // identity permutation (values of the depth sort)
 };
 
-struct ProjectBwdArgs {
-	int P, D, M;
-	const float* means3D;
-	const int* radii;
-	const float* shs;
-	const uint8_t* clamped;
-	const float* scales;
-	const float* rotations;
-	float scale_modifier;
-	const float* cov3D;          // state copy computed by the forward
-	const float* cov3D_precomp;  // or the user's
+// project_bwd.cu: per-Gaussian chain rule for up to MAX_BWD_VIEWS views in one launch
+constexpr int MAX_BWD_VIEWS = 16;
+struct ProjectBwdView {
+	const int* radii;          // [P] of this view
+	const float* gb;           // [P, GB_STRIDE] blend-stage gradients of this view
+	const uint8_t* clamped;    // [P] SH clamp bits of this view (nullable without SHs)
 	const float* viewmatrix;
 	const float* projmatrix;
 	const float* cam_pos;
+	float* dL_dmean2D;         // [P,3] of this view (nullable); with shared_mean2D only view 0's is used and receives the sum
 	float tan_fovx, tan_fovy, focal_x, focal_y;
-	const float* gb;  // [P, GB_STRIDE] blend-stage gradients
-	int accumulate;   // 0: every output row is written once; 1: outputs are summed into with L2 reductions
-	// outputs (each row written exactly once; nullable where noted)
-	float* dL_dmean2D;  // [P,3]
-	float* dL_dconic;   // [P,4] nullable
+};
+struct ProjectBwdViewsArgs {
+	int P, D, M, V;
+	const float* means3D;
+	const float* shs;            // nullable (precomputed colours)
+	const float* scales;         // nullable (precomputed covariance)
+	const float* rotations;
+	float scale_modifier;
+	const float* cov3D_precomp;  // used when scales is null
+	int accumulate;              // 0: every output row is written; 1: added to what the row holds (caller serialises writers)
+	int shared_mean2D;
+	float* dL_dmean3D;  // [P,3]
 	float* dL_dopacity; // [P]
 	float* dL_dcolor;   // [P,3] nullable
-	float* dL_dmean3D;  // [P,3]
 	float* dL_dcov3D;   // [P,6] nullable
 	float* dL_dsh;      // [P,M,3] nullable
 	float* dL_dscale;   // [P,3] nullable
 	float* dL_drot;     // [P,4] nullable
-	float* dL_ddepth;   // [P] nullable
+	float* dL_dconic;   // [P,4] nullable; view 0 only (single-view callers)
+	ProjectBwdView view[MAX_BWD_VIEWS];
 };
 
 struct BlendArgs {
@@ -121,7 +124,7 @@ void launch_activate_fwd(ActivateArgs a, cudaStream_t s);
 void launch_activate_bwd(ActivateArgs a, cudaStream_t s);
 
 void launch_project_fwd(const ProjectFwdArgs& a, cudaStream_t s);
-void launch_project_bwd(const ProjectBwdArgs& a, cudaStream_t s);
+void launch_project_bwd_views(const ProjectBwdViewsArgs& a, cudaStream_t s);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t s);
 
 // binning.cu
@@ -132,11 +135,16 @@ void launch_depth_sort(void* temp, size_t temp_bytes, const uint32_t* depth_bits
 	const uint32_t* iota, uint32_t* order, int P, cudaStream_t s);
 void launch_scan_sorted(void* temp, size_t temp_bytes, const uint32_t* order, const uint32_t* tiles_touched, uint32_t* offsets,
 	int P, cudaStream_t s);
+// capacity: size of the instance arrays; instances beyond it are dropped and *overflow (device, nullable) is set
 void launch_emit_tiles(int P, const uint32_t* order, const float2* means2D, const uint32_t* offsets, const int* radii,
-	uint32_t grid_x, uint32_t grid_y, uint32_t* tile_keys, uint32_t* values, cudaStream_t s);
+	uint32_t grid_x, uint32_t grid_y, uint32_t* tile_keys, uint32_t* values, uint32_t capacity, int* status, cudaStream_t s);
+// instance slots [R, capacity) get the last tile id and an invalid Gaussian id: a stable sort of all `capacity` slots
+// leaves them behind the R real instances (R = offsets[P-1] on the device)
+void launch_fill_tail(const uint32_t* offsets, int P, uint32_t capacity, uint32_t last_tile, uint32_t* tile_keys, uint32_t* values, cudaStream_t s);
 void launch_tile_sort(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
 	const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit, cudaStream_t s);
-void launch_ranges_and_pack(int R, int num_tiles, int grid_x, const uint32_t* tile_keys, const uint32_t* point_list,
+// R < 0: the instance count is read on the device from *R_dev (clamped to `capacity`), the grid covers `capacity`
+void launch_ranges_and_pack(int R, const uint32_t* R_dev, int capacity, int num_tiles, int grid_x, const uint32_t* tile_keys, const uint32_t* point_list,
 	const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs, cudaStream_t s);
 
 // blend_fwd.cu / blend_bwd.cu

@@ -9,8 +9,8 @@ the feature normalisation (:66-68) is the fused sm_100a kernel behind `mgs_activ
 tensor is made when features are absent (:70-71).
 
 `render_views` renders V cameras of ONE Gaussian cloud in a single autograd node: the projection/binning chains of all
-views are enqueued on per-view streams before the host reads the first instance count, every view's backward SUMS its
-per-Gaussian gradients on the device into one packed buffer (`parallel.PackedGradients`), and -- for the view-parallel
+views are enqueued on per-view streams by one C call that never synchronises with the host, every view's backward SUMS its
+per-Gaussian gradients in registers into one packed buffer (`parallel.PackedGradients`), and -- for the view-parallel
 multi-GPU mode -- that buffer is all-reduced with ONE collective before the gradients are handed back to autograd.
 The reference has no counterpart (bs == 1 is asserted, neural_rendering.py:386; one view per call).
 """
@@ -153,8 +153,8 @@ class _RasterizeViews(torch.autograd.Function):
         g_color = _prep(g_color, dev)
         g_feat = _prep(g_feat, dev) if ctx.include else None
         g_depth = _prep(g_depth, dev) if (ctx.return_depth and g_depth is not None and g_depth.numel()) else None
-        pk = PackedGradients(P, ctx.F, M, dev, colors=use_colors)
-        m2d = torch.zeros((V, P, 3), dtype=torch.float32, device=dev)
+        pk = PackedGradients(P, ctx.F, M, dev, colors=use_colors, zero=False)  # every row is written by the backward
+        m2d = torch.empty((V, P, 3), dtype=torch.float32, device=dev)
         outs = [(R, None, None, radii, geom, binb, img) for (R, radii, geom, binb, img) in ctx.state]
         rasterize_views_backward_raw(views, outs, ctx.streams, g_color, g_feat, means3D, colors_precomp if use_colors else None,
                                      feature if ctx.include else None, scales, rotations, views[0].scale_modifier, None,

@@ -140,8 +140,9 @@ def rasterize_gaussians_backward_raw(bg, means3D, radii, colors, language_featur
     dL_dscales, dL_drotations).
 
     accumulate_into: optional dict of preallocated fp32 tensors keyed like manigaussian_b200.parallel.FIELDS
-    (dL_dmeans3D, dL_dmeans2D, dL_dscales, dL_drotations, dL_dopacity, dL_dsh, dL_dfeature); the gradients of this view
-    are then ADDED into them on the device (C ABI `accumulate=1`) and the same tensors are returned."""
+    (dL_dmeans3D, dL_dmeans2D, dL_dscales, dL_drotations, dL_dopacity, dL_dsh, dL_dfeature[, dL_dcolors]); the gradients of
+    this view are then ADDED to what they hold (C ABI `accumulate=1`; calls sharing buffers must be issued on one stream)
+    and the same tensors are returned.  For several views of one cloud prefer rasterize_views_backward_raw."""
     L = _b.lib()
     dev = means3D.device
     P = means3D.size(0)
@@ -159,6 +160,12 @@ def rasterize_gaussians_backward_raw(bg, means3D, radii, colors, language_featur
     opts = dict(dtype=torch.float32, device=dev)
     acc = accumulate_into
     if acc is not None:
+        need = ["dL_dmeans3D", "dL_dmeans2D", "dL_dopacity"]
+        need += ["dL_dscales", "dL_drotations"] if (scales is not None and scales.numel() != 0) else []
+        need += ["dL_dcolors"] if (colors is not None and colors.numel() != 0) else []
+        missing = [k for k in need if acc.get(k) is None]
+        if missing:
+            raise ValueError(f"accumulate_into lacks {missing}: gradients of inputs of this render would be dropped")
         dL_dmeans3D, dL_dmeans2D, dL_dopacity = acc["dL_dmeans3D"], acc["dL_dmeans2D"], acc["dL_dopacity"]
         dL_dscales, dL_drotations = acc.get("dL_dscales"), acc.get("dL_drotations")
         dL_dsh = acc.get("dL_dsh") if M else torch.empty((P, 0, 3), **opts)
@@ -237,6 +244,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         args = (s.bg, means3D, colors_precomp, language_feature_precomp, opacities, scales, rotations, s.scale_modifier,
                 cov3Ds_precomp, s.viewmatrix, s.projmatrix, s.tanfovx, s.tanfovy, s.image_height, s.image_width, sh,
                 s.sh_degree, s.campos, s.prefiltered, s.debug, s.include_feature)
+        ctx.async_view = None
         if s.debug:
             cpu_args = cpu_deep_copy_tuple(args)  # copy before they can be corrupted
             try:
@@ -245,6 +253,14 @@ class _RasterizeGaussians(torch.autograd.Function):
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
+        elif means3D.is_cuda and means3D.size(0) > 0:
+            # no host synchronisation: the binning state is sized from the instance counts of earlier calls (the reference reads
+            # the count back on every call, rasterizer_impl.cu:284); the operator itself never exposes the count
+            outs, streams = rasterize_views_raw([s], means3D, colors_precomp, language_feature_precomp, opacities, scales, rotations,
+                                                s.scale_modifier, cov3Ds_precomp, sh, s.sh_degree, s.include_feature,
+                                                return_depth=return_depth)
+            out = outs[0]
+            ctx.async_view = (outs, streams)
         else:
             out = rasterize_gaussians_raw(*args, return_depth=return_depth)
         num_rendered, color, language_feature, radii, geomBuffer, binningBuffer, imgBuffer = out[:7]
@@ -274,7 +290,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                 grad_out_language_feature, sh, s.sh_degree, s.campos, geomBuffer, ctx.num_rendered, binningBuffer,
                 imgBuffer, s.debug, s.include_feature)
         depth_grad = grad_out_depth if ctx.return_depth else None
-        if s.debug:
+        if ctx.async_view is not None:
+            outs, streams = ctx.async_view
+            grads = rasterize_views_backward_raw(
+                [s], outs, streams, [grad_out_color], [grad_out_language_feature] if s.include_feature else None, means3D,
+                colors_precomp, language_feature_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp, sh, s.sh_degree,
+                s.include_feature, grads_depth=[depth_grad] if depth_grad is not None else None)
+        elif s.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:
                 grads = rasterize_gaussians_backward_raw(*args, dL_dout_depth=depth_grad)
@@ -344,12 +366,18 @@ class GaussianRasterizer(nn.Module):
 
 # ----------------------------------------------------------------------------------------------------------------------
 # Multi-view batches (no counterpart in the reference, which renders one view per call and
-# blocks the host on every view's instance count).  All views share one Gaussian cloud; each view is enqueued on its own
-# CUDA stream through the split forward of the C ABI (mgs_forward_begin / mgs_forward_finish), so the projection and
-# binning chains of all views are in flight before the host waits for the first instance count, and the blend kernels
-# of different views overlap on the GPU.
+# blocks the host on every view's instance count, rasterizer_impl.cu:284).  All views share one Gaussian cloud.  One C
+# call (mgs_forward_views / mgs_backward_views) enqueues every view on its own CUDA stream, forks from and joins back
+# into the caller's current stream, and NEVER synchronises with the host: the per-view binning state is sized from the
+# instance counts observed on earlier calls (plus slack), the real count stays on the device, and {count, overflow flag}
+# come back asynchronously through pinned memory to be looked at on a LATER call.  A step built from these calls
+# allocates through torch's caching allocator only and can be captured in a CUDA graph.
+import warnings
+
 _VIEW_STREAMS = {}
-_PINNED_COUNTS = {}
+_CAPACITY = {}        # (device index, P, W, H, slot) -> instance capacity to use for the next call
+_PENDING_STATUS = []  # [(key, pinned int32[2], cuda event, capacity used)] of forwards whose status has not been read yet
+_SIZES = {}
 
 
 def _view_streams(device, n):
@@ -360,15 +388,98 @@ def _view_streams(device, n):
     return pool[:n]
 
 
+def _round_capacity(n):
+    """geometric buckets (<= 12.5 % slack) so that slowly varying counts keep hitting the same cached allocation"""
+    n = max(int(n), 4096)
+    q = 1 << max(10, n.bit_length() - 4)
+    return (n + q - 1) // q * q
+
+
+def _poll_status(block=False):
+    """Fold the instance counts of finished forwards into the capacity table (never waits unless block=True)."""
+    keep = []
+    for key, st, ev, cap in _PENDING_STATUS:
+        if block:
+            ev.synchronize()
+        if not ev.query():
+            keep.append((key, st, ev, cap))
+            continue
+        R, over = int(st[0]), int(st[1])
+        want = _round_capacity(R * 1.25 + 4096)
+        if over:
+            warnings.warn(f"manigaussian_b200: a view produced {R} tile instances but its binning state held {cap}; the farthest "
+                          f"{R - cap} instances were dropped from that render (capacity raised for the next call)")
+            want = _round_capacity(R * 1.5 + 4096)
+        cur = _CAPACITY.get(key, 0)
+        # grow at once, shrink slowly (a render with few instances must not starve the next one)
+        _CAPACITY[key] = want if want > cur else max(want, int(cur * 0.98))
+    _PENDING_STATUS[:] = keep
+
+
+def reset_capacity_estimates():
+    """Forget the instance-count history (tests; or after a drastic scene change to force re-calibration)."""
+    _poll_status(block=True)
+    _CAPACITY.clear()
+
+
+class ViewOut(tuple):
+    """Result of one view of rasterize_views_raw: (capacity, color, feature, radii, geomBuffer, binningBuffer, imgBuffer
+    [, depth]) -- the layout of rasterize_gaussians_raw with the binning CAPACITY in place of the instance count, which is
+    what the backward needs.  `.num_rendered()` waits for the forward and returns the true count; `.status` is the pinned
+    {count, overflow} pair."""
+    status = None
+    event = None
+
+    def num_rendered(self):
+        self.event.synchronize()
+        return int(self.status[0])
+
+    def overflowed(self):
+        self.event.synchronize()
+        return bool(self.status[1])
+
+
+def _state_sizes(L, P, W, H):
+    key = (P, W, H)
+    s = _SIZES.get(key)
+    if s is None:
+        s = (int(L.mgs_geometry_state_bytes(P)), int(L.mgs_image_state_bytes(W, H)), int(L.mgs_backward_scratch_bytes(P)))
+        _SIZES[key] = s
+    return s
+
+
+def _calibrate(L, views, keys, dev, P, degree, M, means3D, sh, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, debug):
+    """First call for a (cloud size, image size): one projection + scan per view with a host read of the instance count
+    (the reference does this on EVERY call), only to seed the capacity table."""
+    counts = torch.zeros(len(views), dtype=torch.int32).pin_memory()
+    st = torch.cuda.current_stream(dev)
+    keep = []
+    for v, s in enumerate(views):
+        if keys[v] in _CAPACITY:
+            continue
+        H, W = int(s.image_height), int(s.image_width)
+        ga, ia = _Alloc(dev), _Alloc(dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        vm, pm, cp = (_prep(x, dev) for x in (s.viewmatrix, s.projmatrix, s.campos))
+        _b.check(L.mgs_forward_begin(_ALLOC_CB, ga.key, _ALLOC_CB, ia.key, P, int(degree), M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors),
+                                     _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(vm),
+                                     _ptr(pm), _ptr(cp), float(s.tanfovx), float(s.tanfovy), _ptr(radii), counts.data_ptr() + 4 * v,
+                                     int(bool(debug)), st.cuda_stream), "mgs_forward_begin")
+        keep.append((ga.release(), ia.release(), radii, vm, pm, cp))
+    st.synchronize()
+    for v in range(len(views)):
+        if keys[v] not in _CAPACITY:
+            _CAPACITY[keys[v]] = _round_capacity(int(counts[v]) * 1.25 + 4096)
+
+
 def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scales, rotations, scale_modifier, cov3D_precomp,
-                        sh, degree, include_feature, return_depth=False, debug=False, after_view=None, out_buffers=None):
+                        sh, degree, include_feature, return_depth=False, debug=False, out_buffers=None, capacities=None):
     """Forward of V views of one Gaussian cloud.  `views` is a sequence of GaussianRasterizationSettings (bg, viewmatrix,
-    projmatrix, tanfov*, image size, campos are read per view).  Returns (outs, streams): outs[v] has the layout of
-    rasterize_gaussians_raw's result; work of view v is enqueued on streams[v] (callers that consume the outputs on
-    another stream must wait on it; rasterize_views_backward_raw does).  `after_view(v, out)` is called inside view v's
-    stream context as soon as its forward is enqueued (e.g. to enqueue that view's backward before finishing the next view).
+    projmatrix, tanfov*, image size, campos are read per view).  Returns (outs, streams): outs[v] is a ViewOut; all work
+    is joined into the caller's current stream before the call returns (`streams` are the per-view streams used).
     `out_buffers` = (color [V,3,H,W], feature [V,F,H,W] or None, depth [V,H,W] or None): render straight into slices of
-    caller-owned batch tensors instead of per-view allocations."""
+    caller-owned batch tensors instead of per-view allocations.  `capacities` (per-view instance capacities) overrides
+    the history-based sizing of the binning state."""
     L = _b.lib()
     dev = means3D.device
     if not means3D.is_cuda:
@@ -381,86 +492,124 @@ def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scale
     F = language_feature.size(1) if (include_feature and language_feature is not None and language_feature.numel() > 0) else 0
     M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
     V = len(views)
-    streams = _view_streams(dev, V)
     main = torch.cuda.current_stream(dev)
-    counts = _PINNED_COUNTS.get(V)
-    if counts is None or counts.numel() < V:
-        counts = torch.zeros(max(V, 8), dtype=torch.int32).pin_memory()
-        _PINNED_COUNTS[V] = counts
-    pend = []
+    streams = _view_streams(dev, V) if V > 1 else [main]  # a single view needs no side stream
+    di = dev.index if dev.index is not None else torch.cuda.current_device()
+    keys = [(di, P, int(s.image_width), int(s.image_height), v) for v, s in enumerate(views)]
     with torch.cuda.device(dev):
+        _poll_status()
+        if capacities is None and any(k not in _CAPACITY for k in keys):
+            _calibrate(L, views, keys, dev, P, degree, M, means3D, sh, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                       debug)
+        arr = (_b.View * V)()
+        status = torch.zeros((V, 2), dtype=torch.int32).pin_memory()
+        keep, outs = [], []
         for v, s in enumerate(views):
-            st = streams[v]
-            st.wait_stream(main)
-            with torch.cuda.stream(st):
-                H, W = int(s.image_height), int(s.image_width)
-                bg, vm, pm, cp = (_prep(x, dev) for x in (s.bg, s.viewmatrix, s.projmatrix, s.campos))
-                radii = torch.empty((P,), dtype=torch.int32, device=dev)
-                ga, ia, ba = _Alloc(dev), _Alloc(dev), _Alloc(dev)
-                _b.check(L.mgs_forward_begin(
-                    _ALLOC_CB, ga.key, _ALLOC_CB, ia.key, P, int(degree), M, W, H,
-                    _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations),
-                    _ptr(cov3D_precomp), _ptr(vm), _ptr(pm), _ptr(cp), float(s.tanfovx), float(s.tanfovy), _ptr(radii),
-                    counts.data_ptr() + 4 * v, int(bool(debug)), st.cuda_stream), "mgs_forward_begin")
-                pend.append((st, H, W, bg, vm, pm, cp, radii, ga, ia, ba))
-        # binning of every view first (short kernels), then every view's blend (long kernels): a view's binning chain is
-        # never queued behind another view's blend
-        mid = []
-        for v, (st, H, W, bg, vm, pm, cp, radii, ga, ia, ba) in enumerate(pend):
-            st.synchronize()
-            R = int(counts[v])
-            with torch.cuda.stream(st):
-                geom, img = ga.release(), ia.release()
-                _b.check(L.mgs_forward_finish(
-                    _ALLOC_CB, ba.key, None, _ptr(geom), _ptr(img), P, 0, W, H, _ptr(bg), None, _ptr(radii), R,
-                    _ptr(radii), None, None, 1, int(bool(debug)), st.cuda_stream), "mgs_forward_finish(binning)")
-                mid.append((R, geom, img, ba.release()))
-        outs = []
-        for v, (st, H, W, bg, vm, pm, cp, radii, ga, ia, ba) in enumerate(pend):
-            R, geom, img, binb = mid[v]
-            with torch.cuda.stream(st):
-                if out_buffers is not None:
-                    out_color = out_buffers[0][v]
-                    out_feature = out_buffers[1][v] if (include_feature and F) else torch.zeros((1,), dtype=torch.float32, device=dev)
-                    out_depth = out_buffers[2][v] if return_depth else None
-                else:
-                    out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-                    out_feature = torch.empty((F, H, W), dtype=torch.float32, device=dev) if include_feature else \
-                        torch.zeros((1,), dtype=torch.float32, device=dev)
-                    out_depth = torch.empty((H, W), dtype=torch.float32, device=dev) if return_depth else None
-                _b.check(L.mgs_forward_finish(
-                    _ALLOC_CB, None, _ptr(binb), _ptr(geom), _ptr(img), P, F, W, H, _ptr(bg), _ptr(language_feature) if F else None,
-                    _ptr(radii), R, _ptr(out_color), _ptr(out_feature) if F else None, _ptr(out_depth), 2, int(bool(debug)),
-                    st.cuda_stream), "mgs_forward_finish(blend)")
-                ret = (R, out_color, out_feature, radii, geom, binb, img)
-                outs.append(ret + (out_depth,) if return_depth else ret)
-                if after_view is not None:
-                    after_view(v, outs[-1])  # still inside view v's stream context
+            H, W = int(s.image_height), int(s.image_width)
+            cap = int(capacities[v]) if capacities is not None else _CAPACITY[keys[v]]
+            gbytes, ibytes, _ = _state_sizes(L, P, W, H)
+            geom = torch.empty(gbytes, dtype=torch.uint8, device=dev)
+            img = torch.empty(ibytes, dtype=torch.uint8, device=dev)
+            binb = torch.empty(int(L.mgs_binning_state_bytes(cap)), dtype=torch.uint8, device=dev)
+            radii = torch.empty((P,), dtype=torch.int32, device=dev)
+            bg, vm, pm, cp = (_prep(x, dev) for x in (s.bg, s.viewmatrix, s.projmatrix, s.campos))
+            if out_buffers is not None:
+                out_color = out_buffers[0][v]
+                out_feature = out_buffers[1][v] if (include_feature and F) else torch.zeros((1,), dtype=torch.float32, device=dev)
+                out_depth = out_buffers[2][v] if return_depth else None
+            else:
+                out_color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+                out_feature = torch.empty((F, H, W), dtype=torch.float32, device=dev) if include_feature else \
+                    torch.zeros((1,), dtype=torch.float32, device=dev)
+                out_depth = torch.empty((H, W), dtype=torch.float32, device=dev) if return_depth else None
+            w = arr[v]
+            w.viewmatrix, w.projmatrix, w.cam_pos, w.background = _ptr(vm), _ptr(pm), _ptr(cp), _ptr(bg)
+            w.tan_fovx, w.tan_fovy, w.width, w.height = float(s.tanfovx), float(s.tanfovy), W, H
+            w.geometry_state, w.binning_state, w.image_state, w.binning_capacity = geom.data_ptr(), binb.data_ptr(), img.data_ptr(), cap
+            w.out_color, w.out_feature, w.out_depth, w.radii = _ptr(out_color), (_ptr(out_feature) if F else None), _ptr(out_depth), _ptr(radii)
+            w.status = status.data_ptr() + 8 * v
+            w.stream = streams[v].cuda_stream
+            keep.append((bg, vm, pm, cp))
+            ret = (cap, out_color, out_feature, radii, geom, binb, img) + ((out_depth,) if return_depth else ())
+            outs.append(ViewOut(ret))
+        _b.check(L.mgs_forward_views(V, arr, P, int(degree), M, F, _ptr(means3D), _ptr(sh), _ptr(colors),
+                                     _ptr(language_feature) if F else None, _ptr(opacity), _ptr(scales), float(scale_modifier),
+                                     _ptr(rotations), _ptr(cov3D_precomp), 0, int(bool(debug)), main.cuda_stream), "mgs_forward_views")
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for v, o in enumerate(outs):
+            o.status, o.event = status[v], ev
+            if capacities is None:
+                _PENDING_STATUS.append((keys[v], status[v], ev, o[0]))
     return outs, streams
 
 
 def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_feature, means3D, colors, language_feature, scales,
                                  rotations, scale_modifier, cov3D_precomp, sh, degree, include_feature, grads_depth=None,
-                                 debug=False, accumulate_into=None, means2D_per_view=None):
-    """Backward of the V views rendered by rasterize_views_raw, each on its view's stream.  Returns a list of the
-    9-tuples of rasterize_gaussians_backward_raw.  The caller's current stream waits for all of them on return.
-    With `accumulate_into`, `means2D_per_view` (zeroed [V,P,3]) keeps the screen-space gradients of each view apart
-    (the reference's per-render `viewspace_points.grad`) while everything else is summed over views."""
+                                 debug=False, accumulate_into=None, means2D_per_view=None, accumulate=False):
+    """Backward of the V views rendered by rasterize_views_raw: every view's blend backward on its stream, then ONE
+    per-Gaussian chain-rule kernel that sums over the views (mgs_backward_views).  Returns the 9-tuple of
+    rasterize_gaussians_backward_raw holding the SUMS over the views (dL_dmeans2D: `means2D_per_view` [V,P,3] when given,
+    else the sum).  `accumulate_into`: dict of preallocated fp32 tensors keyed like manigaussian_b200.parallel.FIELDS that
+    receive the sums (e.g. the views of a PackedGradients buffer -- the all-reduce message); rows are overwritten unless
+    accumulate=True.  The caller's current stream holds the result on return."""
+    L = _b.lib()
     dev = means3D.device
+    P = means3D.size(0)
+    means3D, colors, language_feature = (_prep(x, dev) for x in (means3D, colors, language_feature))
+    scales, rotations, cov3D_precomp, sh = (_prep(x, dev) for x in (scales, rotations, cov3D_precomp, sh))
+    F = language_feature.size(1) if (include_feature and language_feature is not None and language_feature.numel() > 0) else 0
+    M = sh.size(1) if (sh is not None and sh.numel() != 0) else 0
+    V = len(views)
     main = torch.cuda.current_stream(dev)
-    res = []
-    for v, s in enumerate(views):
-        st = streams[v]
-        st.wait_stream(main)
-        with torch.cuda.stream(st):
+    opts = dict(dtype=torch.float32, device=dev)
+    acc = accumulate_into or {}
+    has_sr = scales is not None and scales.numel() != 0
+    use_colors = colors is not None and colors.numel() != 0
+
+    def out(name, shape, need=True):
+        t = acc.get(name)
+        if t is None and need:
+            if accumulate_into is not None and name not in ("dL_dmeans2D", "dL_dcov3D"):
+                raise ValueError(f"accumulate_into lacks '{name}', the gradient of an input of this render")
+            t = torch.empty(shape, **opts)
+        return t
+
+    dL_dmeans3D = out("dL_dmeans3D", (P, 3))
+    dL_dopacity = out("dL_dopacity", (P, 1))
+    dL_dscales = out("dL_dscales", (P, 3), has_sr)
+    dL_drotations = out("dL_drotations", (P, 4), has_sr)
+    dL_dsh = out("dL_dsh", (P, M, 3), M > 0)
+    dL_dfeature = out("dL_dfeature", (P, F), F > 0)
+    dL_dcolors = out("dL_dcolors", (P, 3), use_colors)
+    dL_dcov3D = out("dL_dcov3D", (P, 6), cov3D_precomp is not None and cov3D_precomp.numel() != 0)
+    shared = means2D_per_view is None
+    m2d = out("dL_dmeans2D", (P, 3)) if shared else means2D_per_view
+    with torch.cuda.device(dev):
+        arr = (_b.View * V)()
+        keep = []
+        for v, s in enumerate(views):
             o = outs[v]
-            res.append(rasterize_gaussians_backward_raw(
-                s.bg, means3D, o[3], colors, language_feature, scales, rotations, scale_modifier, cov3D_precomp, s.viewmatrix,
-                s.projmatrix, s.tanfovx, s.tanfovy, grads_color[v], grads_feature[v] if grads_feature is not None else None, sh,
-                degree, s.campos, o[4], o[0], o[5], o[6], debug, include_feature,
-                dL_dout_depth=grads_depth[v] if grads_depth is not None else None,
-                accumulate_into=(dict(accumulate_into, dL_dmeans2D=means2D_per_view[v])
-                                 if (accumulate_into is not None and means2D_per_view is not None) else accumulate_into)))
-    for st in streams[:len(views)]:
-        main.wait_stream(st)
-    return res
+            H, W = int(s.image_height), int(s.image_width)
+            bg, vm, pm, cp = (_prep(x, dev) for x in (s.bg, s.viewmatrix, s.projmatrix, s.campos))
+            gc = _prep(grads_color[v], dev)
+            gf = _prep(grads_feature[v], dev) if (F and grads_feature is not None) else None
+            gd = _prep(grads_depth[v], dev) if grads_depth is not None else None
+            scratch = torch.empty((_state_sizes(L, P, W, H)[2],), dtype=torch.uint8, device=dev)
+            w = arr[v]
+            w.viewmatrix, w.projmatrix, w.cam_pos, w.background = _ptr(vm), _ptr(pm), _ptr(cp), _ptr(bg)
+            w.tan_fovx, w.tan_fovy, w.width, w.height = float(s.tanfovx), float(s.tanfovy), W, H
+            w.geometry_state, w.binning_state, w.image_state, w.binning_capacity = o[4].data_ptr(), o[5].data_ptr(), o[6].data_ptr(), int(o[0])
+            w.radii = _ptr(o[3])
+            w.dL_dpix, w.dL_dpix_F, w.dL_dpix_depth = _ptr(gc), _ptr(gf), _ptr(gd)
+            w.blend_scratch = scratch.data_ptr()
+            w.dL_dmean2D = _ptr(m2d) if shared else _ptr(m2d[v])
+            w.stream = streams[v].cuda_stream
+            keep.append((bg, vm, pm, cp, gc, gf, gd, scratch))
+        _b.check(L.mgs_backward_views(V, arr, P, int(degree), M, F, _ptr(means3D), _ptr(sh) if M else None, _ptr(colors),
+                                      _ptr(language_feature) if F else None, _ptr(scales), float(scale_modifier), _ptr(rotations),
+                                      _ptr(cov3D_precomp), _ptr(dL_dmeans3D), _ptr(dL_dopacity), _ptr(dL_dcolors),
+                                      _ptr(dL_dfeature) if F else None, _ptr(dL_dcov3D), _ptr(dL_dsh) if M else None,
+                                      _ptr(dL_dscales) if has_sr else None, _ptr(dL_drotations) if has_sr else None,
+                                      int(shared), int(bool(accumulate)), int(bool(debug)), main.cuda_stream), "mgs_backward_views")
+    return (m2d, dL_dcolors, dL_dfeature, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)

@@ -18,7 +18,11 @@ things the reference tree lacks are supplied from the command line instead of by
 
 Usage:  python oracle/build_ref.py [3 32 ...]     (default: 3 and 32)
 Outputs: oracle/_ref/dgr_ref_f<F>/dgr_ref_f<F>.so  (pybind module exporting
-rasterize_gaussians / rasterize_gaussians_backward / mark_visible, DGR/ext.cpp:14-18).
+rasterize_gaussians / rasterize_gaussians_backward / mark_visible, DGR/ext.cpp:14-18), and
+oracle/_ref/python/diff_gaussian_rasterization/__init__.py -- the reference's own Python operator
+(autograd.Function, GaussianRasterizer), INSTALLED there unmodified like `pip install` would (oracle/_ref is
+build output: git-ignored, never committed), so that bench.py's reference arm drives the reference's own
+wrapper on the GPU box where /root/reference does not exist (tests/util.py::load_reference_package).
 """
 import os
 import sys
@@ -65,6 +69,11 @@ def main(argv):
         print(f"[build_ref] {REF_ROOT} not present (GPU box) -- using prebuilt oracle/_ref if any")
         return 0
     variants = [int(a) for a in argv] or [3, 32]
+    import shutil
+    pkg = os.path.join(OUT, "python", "diff_gaussian_rasterization")
+    os.makedirs(pkg, exist_ok=True)
+    shutil.copyfile(os.path.join(REF_ROOT, "diff_gaussian_rasterization", "__init__.py"), os.path.join(pkg, "__init__.py"))
+    print(f"[build_ref] installed the reference's Python operator into {pkg}")
     for F in variants:
         m = build_variant(F, verbose=True)
         print(f"[build_ref] built {m.__file__}")

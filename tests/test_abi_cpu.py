@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for sym in sorted(declared):
         assert hasattr(L, sym), f"{sym} declared in include/mgs_rasterizer.h but not exported"
     assert declared == set(_binding.EXPORTED_SYMBOLS)
-    assert L.mgs_abi_version() == 102
+    assert L.mgs_abi_version() == 200
 
 
 def test_state_size_queries_are_monotone_and_aligned():

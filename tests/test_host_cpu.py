@@ -79,7 +79,8 @@ def test_packed_gradient_buffer_layout():
         assert (v.data_ptr() - base) % 16 == 0, k
         assert v.shape == (P, pk.widths[k]) and v.is_contiguous()
     assert "dL_dcolors" not in pk.views and set(pk.views) <= set(FIELDS)
-    assert pk.bytes_per_gaussian == 4 * (3 + 3 + 3 + 4 + 1 + 3 * M + F)
+    assert pk.bytes_per_gaussian == 4 * (3 + 3 + 4 + 1 + 3 * M + F)  # the per-view screen-space gradients are not in the message
+    assert "dL_dmeans2D" not in pk.views and "dL_dmeans2D" in PackedGradients(P, F, M, "cpu", means2D=True).views
     assert "dL_dcolors" in PackedGradients(P, 0, 0, "cpu", colors=True).views
     # fields do not overlap
     spans = sorted((v.data_ptr(), v.data_ptr() + v.numel() * 4) for v in pk.views.values())

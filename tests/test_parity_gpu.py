@@ -264,9 +264,10 @@ def test_full_size_properties_c3():
 
 
 def test_multi_view_api_and_accumulate_mode():
-    """rasterize_views_raw (split forward, one stream per view) must reproduce the single-view entry point bit for bit,
-    and the accumulate mode must equal the sum of the per-view gradients (sum over views on one GPU ==
-    what the all-reduce produces across GPUs)."""
+    """rasterize_views_raw (one C call, one stream per view, no host synchronisation, binning state sized from the instance
+    counts of earlier calls) must reproduce the single-view entry point bit for bit, and the multi-view backward (sum over
+    views in registers) must equal the sum of the per-view gradients (sum over views on one GPU == what the
+    all-reduce produces across GPUs).  Also: an undersized binning state is reported, not fatal."""
     import torch
     from manigaussian_b200 import rasterizer as R
     from manigaussian_b200 import GaussianRasterizationSettings as S
@@ -280,25 +281,40 @@ def test_multi_view_api_and_accumulate_mode():
     views = [S(H, W, i["cam"]["tanfovx"], i["cam"]["tanfovy"], t(i["bg"]), 1.0, t(i["cam"]["viewmatrix"]), t(i["cam"]["projmatrix"]), 1,
                t(i["cam"]["campos"]), False, False, True) for i in inps]
     cts = [(t(i["ct"]["dL_dcolor"]), t(i["ct"]["dL_dfeature"])) for i in inps]
-    outs, sts = R.rasterize_views_raw(views, G["means3D"], e, G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0, e, G["shs"], 1, True)
-    pk = PackedGradients(P, F, 4, "cuda")
+    R.reset_capacity_estimates()
+    for rep in range(2):  # first call calibrates the capacities with a host read, the second runs on the history alone
+        outs, sts = R.rasterize_views_raw(views, G["means3D"], e, G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0, e, G["shs"], 1, True)
+    pk = PackedGradients(P, F, 4, "cuda", zero=False)
+    m2d = torch.empty((V, P, 3), device="cuda")
     R.rasterize_views_backward_raw(views, outs, sts, [c[0] for c in cts], [c[1] for c in cts], G["means3D"], e, G["feature"], G["scales"],
-                                   G["rotations"], 1.0, e, G["shs"], 1, True, accumulate_into=pk.views)
+                                   G["rotations"], 1.0, e, G["shs"], 1, True, accumulate_into=pk.views, means2D_per_view=m2d)
+    summed = R.rasterize_views_backward_raw(views, outs, sts, [c[0] for c in cts], [c[1] for c in cts], G["means3D"], e, G["feature"],
+                                            G["scales"], G["rotations"], 1.0, e, G["shs"], 1, True)
     torch.cuda.synchronize()
     names = ("dL_dmeans2D", "dL_dcolors", "dL_dfeature", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations")
     total = {}
     for v, s in enumerate(views):
         single = R.rasterize_gaussians_raw(s.bg, G["means3D"], e, G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0, e, s.viewmatrix,
                                            s.projmatrix, s.tanfovx, s.tanfovy, H, W, G["shs"], 1, s.campos, False, False, True)
-        assert single[0] == outs[v][0]
+        assert single[0] == outs[v].num_rendered() and not outs[v].overflowed() and outs[v][0] >= single[0]
         assert torch.equal(single[1], outs[v][1]) and torch.equal(single[2], outs[v][2]) and torch.equal(single[3], outs[v][3])
         gr = R.rasterize_gaussians_backward_raw(s.bg, G["means3D"], single[3], e, G["feature"], G["scales"], G["rotations"], 1.0, e, s.viewmatrix,
                                                 s.projmatrix, s.tanfovx, s.tanfovy, cts[v][0], cts[v][1], G["shs"], 1, s.campos, single[4],
                                                 single[0], single[5], single[6], False, True)
+        assert util.rel_l2(m2d[v].cpu().numpy(), gr[0].cpu().numpy()) < 1e-5
         for n, x in zip(names, gr):
             total[n] = x.double() if n not in total else total[n] + x.double()
     for k, view in pk.views.items():
         assert util.rel_l2(view.cpu().numpy(), total[k].reshape(view.shape).cpu().numpy()) < 1e-5, k
+    for n, x in zip(names, summed):
+        if x is not None and n in total and n not in ("dL_dcolors", "dL_dcov3D"):
+            assert util.rel_l2(x.cpu().numpy(), total[n].reshape(x.shape).cpu().numpy()) < 1e-5, n
+    # an undersized binning state: the overflow is flagged and the farthest instances are dropped, nothing else breaks
+    small = [max(1024, outs[v].num_rendered() // 2) for v in range(V)]
+    with torch.no_grad():
+        o2, _ = R.rasterize_views_raw(views, G["means3D"], e, G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0, e, G["shs"], 1, True,
+                                      capacities=small)
+    assert all(o.overflowed() for o in o2) and all(torch.isfinite(o[1]).all() for o in o2)
 
 
 def test_dynamic_path_gradients_reach_deformation_offsets():

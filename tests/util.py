@@ -50,6 +50,25 @@ def load_reference(F):
     return mod
 
 
+def load_reference_package(F):
+    """The reference's OWN Python operator (diff_gaussian_rasterization/__init__.py, installed unmodified into
+    oracle/_ref/python by oracle/build_ref.py) bound to the compiled reference of feature width F: its `from . import _C`
+    resolves to that build.  Returns the package module (GaussianRasterizer, GaussianRasterizationSettings) or None."""
+    mod = load_reference(F)
+    init = os.path.join(ROOT, "oracle", "_ref", "python", "diff_gaussian_rasterization", "__init__.py")
+    if mod is None or not os.path.exists(init):
+        return None
+    name = f"dgr_reference_pkg_f{F}"
+    if name in sys.modules:
+        return sys.modules[name]
+    sys.modules[name + "._C"] = mod
+    spec = importlib.util.spec_from_file_location(name, init, submodule_search_locations=[os.path.dirname(init)])
+    pkg = importlib.util.module_from_spec(spec)
+    sys.modules[name] = pkg
+    spec.loader.exec_module(pkg)
+    return pkg
+
+
 def _obtain(base_ptr, off, nbytes, align=128):
     a = (base_ptr + off + align - 1) & ~(align - 1)
     return a - base_ptr, a - base_ptr + nbytes

@@ -10,5 +10,5 @@ import json
 for t in ('ours','ref'):
     d=json.load(open('gpurun_out/bench_default_%s.json'%t))
     print(t,'value %.4g ms/step %.3f'%(d['value'],d['ms_per_step']),'e2e',d.get('e2e',{}).get('value'),'launches',d.get('gpu_launches'))
-    print('   roofline',d.get('roofline')); print('   cpu',d.get('cpu_baseline')); print('   clocks',d.get('clocks')); print('   stages',d['config'].get('stage_ms_per_launch'))
+    print('   roofline',d.get('roofline')); print('   cpu',d.get('cpu_baseline')); print('   clocks',d.get('clocks')); print('   stages',(d.get('measured') or d['config']).get('stage_ms_per_launch'))
 PY

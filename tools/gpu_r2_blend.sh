@@ -8,7 +8,7 @@ run() { tag=$1; shift; timeout 300 python bench.py --workload ${WL:-c3} --no-e2e
 python - <<PY
 import json
 try:
-    d=json.load(open('gpurun_out/r2b_$tag.json')); s=d['config'].get('stage_ms_per_launch') or {}
+    d=json.load(open('gpurun_out/r2b_$tag.json')); s=(d.get('measured') or d['config']).get('stage_ms_per_launch') or {}
     print('$tag: %.4g G/s  %.3f ms/step  fwd %.4f bwd %.4f'%(d['value'],d['ms_per_step'],s.get('blend_fwd',0),s.get('blend_bwd',0)), {k:v for k,v in s.items() if not k.startswith('blend') and v})
 except Exception as e: print('$tag: no json', e)
 PY

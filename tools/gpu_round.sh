@@ -10,7 +10,7 @@ try:
     d=json.load(open('gpurun_out/bench_$1_$2.json'))
     print('$1 $2 value %.4g ms/step %.3f'%(d['value'],d['ms_per_step']),'e2e %.4g'%d.get('e2e',{}).get('value',0),'launches',d.get('gpu_launches'))
     print('   roofline', d.get('roofline'))
-    print('   stages', d['config'].get('stage_ms_per_launch'))
+    print('   stages', (d.get('measured') or d['config']).get('stage_ms_per_launch'))
 except Exception as e: print('no json', e)
 PY
 done

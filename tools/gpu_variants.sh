@@ -13,7 +13,7 @@ for spec in "${VS[@]}"; do
 import json
 try:
     d=json.load(open('gpurun_out/var_${v}_$w.json'))
-    s=d['config'].get('stage_ms_per_launch') or {}
+    s=(d.get('measured') or d['config']).get('stage_ms_per_launch') or {}
     print('variant $v [$defs] $w: %.4g G/s  %.3f ms/step  fwd %.4f bwd %.4f'%(d['value'],d['ms_per_step'],s.get('blend_fwd',0),s.get('blend_bwd',0)))
 except Exception as e: print('variant $v $w: no json', e)
 PY
