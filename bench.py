@@ -208,11 +208,15 @@ GRAD_ORDER = ("dL_dmeans2D", "dL_dcolors", "dL_dfeature", "dL_dopacity", "dL_dme
 PACKED = ("dL_dmeans3D", "dL_dmeans2D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dsh", "dL_dfeature")
 
 
-def make_packed(P, F, M, torch):
+def make_packed(P, F, M, torch, registered=False):
     """One flat fp32 buffer holding every per-Gaussian gradient the optimiser needs; the all-reduce message."""
     from manigaussian_b200.parallel import PackedGradients
-    pk = PackedGradients(P, F, M, "cuda")
+    pk = PackedGradients(P, F, M, "cuda", registered=registered)
+    _PACKS[pk.flat.data_ptr()] = pk
     return pk.flat, pk.views
+
+
+_PACKS = {}
 
 
 def run_step_views(G, C, T, flat, acc, dist, F, depth):
@@ -227,12 +231,14 @@ def run_step_views(G, C, T, flat, acc, dist, F, depth):
     views = G["settings"]
     outs, sts = R.rasterize_views_raw(views, G["means3D"], G["empty"], G["feature"], G["opacities"], G["scales"], G["rotations"], 1.0,
                                       G["empty"], G["shs"], SH_DEGREE, F > 0, return_depth=depth)
+    pk = _PACKS[flat.data_ptr()] if dist is not None else None
     R.rasterize_views_backward_raw(views, outs, sts, [t["dL_dcolor"] for t in T],
                                    [t["dL_dfeature"] for t in T] if F else None, G["means3D"], G["empty"], G["feature"],
                                    G["scales"], G["rotations"], 1.0, G["empty"], G["shs"], SH_DEGREE, F > 0,
-                                   grads_depth=[t["dL_ddepth"] for t in T] if depth else None, accumulate_into=acc)
-    if dist is not None:
-        dist.all_reduce(flat)
+                                   grads_depth=[t["dL_ddepth"] for t in T] if depth else None, accumulate_into=acc,
+                                   after_blend=pk.all_reduce_begin if pk is not None else None)
+    if pk is not None:
+        pk.all_reduce_finish()  # the rest of the ONE packed message; the feature field left while the last kernel ran
     G["last_outs"] = outs  # instance counts are read after the timed region (no host synchronisation inside it)
     return 0
 
@@ -692,7 +698,7 @@ def strong_scaling_c5(torch, dist, rank, world, steps, warmup):
         return to_device(g, cams, cts, torch)
 
     G, C, T = dev_views(mine)
-    flat, acc = make_packed(P, F, M, torch)
+    flat, acc = make_packed(P, F, M, torch, registered=world > 1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -763,7 +769,7 @@ def main():
            "feature_channels": wl["F"], "depth": wl["depth"], "sh_degree": SH_DEGREE,
            "parallelism": f"view-parallel x{world}, 1 NCCL all-reduce of packed per-Gaussian grads per step" if world > 1 else "1 GPU"}
 
-    if world > 1 and rank == 0 and "NCCL_DEBUG" not in os.environ:
+    if world > 1 and rank == 0 and "NCCL_DEBUG_FILE" not in os.environ:
         # record which algorithms/transports NCCL sets up (NVLS = in-switch reduction over NVSwitch) next to the numbers;
         # must be in the environment before the NCCL library initialises its logging
         os.environ["MGS_NCCL_LOG"] = f"/tmp/mgs_nccl_{os.getpid()}.log"
@@ -806,14 +812,19 @@ def main():
     g, cams, cts = host_inputs(wl, rank, world)
     G, C, T = to_device(g, cams, cts, torch)
     impl = Impl(F, wl["depth"]) if a.impl == "ours" else RefImpl(F, wl["depth"])
-    flat, acc = make_packed(P, F, M, torch)
+    flat, acc = make_packed(P, F, M, torch, registered=(world > 1 and a.impl == "ours"))
     packed_bytes = int(flat.numel() * 4)
+    pk0 = _PACKS.get(flat.data_ptr())
 
     streams = None
     if a.impl == "ours" and a.streams > 1 and V > 1:
         streams = [torch.cuda.Stream() for _ in range(min(a.streams, V))]
     cfg["view_streams"] = len(streams) if streams else 1
     meas = {}  # everything MEASURED goes here, `config` only names the workload
+    if world > 1 and pk0 is not None:
+        meas["packed_buffer_nccl_registered"] = bool(pk0.registered)
+        if getattr(pk0, "registration_error", None):
+            meas["packed_buffer_registration_error"] = pk0.registration_error[:200]
 
     def barrier():
         torch.cuda.synchronize()
@@ -977,6 +988,8 @@ def main():
         out["e2e"] = e2e
     if c5 is not None:
         out["c5"] = c5
+    if world > 1:
+        meas["nccl_env"] = {k: v for k, v in os.environ.items() if k.startswith("NCCL_")}
     if nccl_log and os.path.exists(nccl_log):
         try:
             lines = [ln.strip() for ln in open(nccl_log, errors="replace") if any(k in ln for k in ("NVLS", "NCCL version", "Using network", "Channel", "nRanks", "P2P", "Ring", "Tree", "TUNING"))]

@@ -210,6 +210,8 @@ int mgs_backward(
  * kernel that sums over the views in registers: outputs are the SUMS over the V views (the packed buffer of the
  * multi-GPU all-reduce can be passed directly), except dL_dmean2D which each view owns ([P,3], shared_mean2D = 0) or
  * which is summed into views[0].dL_dmean2D (shared_mean2D = 1).  Output NULL-ability as in mgs_backward.
+ * `stages` splits the call in two so that a multi-GPU caller can start the all-reduce of dL_dfeature -- more than half of
+ * the message, final after the blend stage -- while the per-Gaussian stage computes the remaining fields.
  */
 typedef struct mgs_view {
 	const float* viewmatrix;     /* device, 16 floats */
@@ -271,6 +273,7 @@ int mgs_backward_views(
 	float* dL_drot,
 	int shared_mean2D,
 	int accumulate,
+	int stages,            /* 1: blend stage of every view (dL_dfeature is final afterwards), 2: the per-Gaussian stage, 3: both */
 	int debug,
 	void* join_stream);
 

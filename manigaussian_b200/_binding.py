@@ -80,7 +80,7 @@ def lib():
                                      vp, vp, vp, vp,                    # means3D shs colors feature
                                      vp, f, vp, vp,                     # scales scale_modifier rotations cov3D_precomp
                                      vp, vp, vp, vp, vp, vp, vp, vp,    # dL: mean3D opacity color feature cov3D sh scale rot
-                                     i, i, i, vp]                       # shared_mean2D accumulate debug join_stream
+                                     i, i, i, i, vp]                    # shared_mean2D accumulate stages debug join_stream
     L.mgs_mark_visible.restype = C.c_int
     L.mgs_mark_visible.argtypes = [i, vp, vp, vp, vp, vp]
     L.mgs_state_array.restype = C.c_int

@@ -593,9 +593,10 @@ int mgs_backward_views(
 	const float* means3D, const float* shs, const float* colors_precomp, const float* feature_precomp,
 	const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
 	float* dL_dmean3D, float* dL_dopacity, float* dL_dcolor, float* dL_dfeature, float* dL_dcov3D, float* dL_dsh,
-	float* dL_dscale, float* dL_drot, int shared_mean2D, int accumulate, int debug, void* join_stream)
+	float* dL_dscale, float* dL_drot, int shared_mean2D, int accumulate, int stages, int debug, void* join_stream)
 {
 	(void)colors_precomp;
+	if (!(stages & 3)) return fail(MGS_ERR_INVALID_ARG, "stages must name the blend stage (1), the per-Gaussian stage (2) or both (3)");
 	if (V <= 0 || !views) return fail(MGS_ERR_INVALID_ARG, "need at least one view");
 	if (P <= 0) return fail(MGS_ERR_INVALID_ARG, "P must be > 0");
 	if (!means3D || !dL_dmean3D || !dL_dopacity) return fail(MGS_ERR_INVALID_ARG, "means3D, dL_dmean3D and dL_dopacity are required");
@@ -609,12 +610,14 @@ int mgs_backward_views(
 		if (F > 0 && !w.dL_dpix_F) return fail(MGS_ERR_INVALID_ARG, "view: dL_dpix_F is required with features");
 	}
 	cudaStream_t join = reinterpret_cast<cudaStream_t>(join_stream);
+	int rc = 0;
+	if (stages & 1) {
 	{
 		cudaStream_t st = join;  // for MGS_CUDA's messages
 		(void)st;
 		if (F > 0 && !accumulate) MGS_CUDA(cudaMemsetAsync(dL_dfeature, 0, (size_t)P * F * sizeof(float), join));
 	}
-	int rc = fork_streams(V, views, join);
+	rc = fork_streams(V, views, join);
 	if (rc < 0) return rc;
 	// blend stage of every view on its own stream: per-view blend-stage records, feature gradients summed with 128-bit
 	// reductions straight into dL_dfeature
@@ -645,6 +648,8 @@ int mgs_backward_views(
 	}
 	rc = join_streams(V, views, join);
 	if (rc < 0) return rc;
+	}  // blend stage: dL_dfeature is final here -- a caller may start exchanging it while the per-Gaussian stage runs
+	if (!(stages & 2)) return 0;
 	// one launch per MAX_BWD_VIEWS views: the per-Gaussian chain rule, summed over the views in registers
 	const bool have_sr = scales && rotations && dL_dscale && dL_drot;
 	for (int v0 = 0; v0 < V; v0 += MAX_BWD_VIEWS) {

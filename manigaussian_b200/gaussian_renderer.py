@@ -154,15 +154,18 @@ class _RasterizeViews(torch.autograd.Function):
         g_feat = _prep(g_feat, dev) if ctx.include else None
         g_depth = _prep(g_depth, dev) if (ctx.return_depth and g_depth is not None and g_depth.numel()) else None
         pk = PackedGradients(P, ctx.F, M, dev, colors=use_colors, zero=False)  # every row is written by the backward
+        grp = None if ctx.group in (None, True) else ctx.group
         m2d = torch.empty((V, P, 3), dtype=torch.float32, device=dev)
         outs = [(R, None, None, radii, geom, binb, img) for (R, radii, geom, binb, img) in ctx.state]
         rasterize_views_backward_raw(views, outs, ctx.streams, g_color, g_feat, means3D, colors_precomp if use_colors else None,
                                      feature if ctx.include else None, scales, rotations, views[0].scale_modifier, None,
                                      sh if M else None, ctx.degree, ctx.include, grads_depth=g_depth, debug=views[0].debug,
-                                     accumulate_into=pk.views, means2D_per_view=m2d)
+                                     accumulate_into=pk.views, means2D_per_view=m2d,
+                                     after_blend=(lambda: pk.all_reduce_begin(grp)) if ctx.group is not None else None)
         if ctx.group is not None:
-            # view-parallel multi-GPU: the one exchange of the path, a single SUM all-reduce of the packed buffer
-            pk.all_reduce(None if ctx.group is True else ctx.group)
+            # view-parallel multi-GPU: the one exchange of the path, a SUM all-reduce of the packed buffer; the feature field
+            # (final after the blend stage) is already travelling while the per-Gaussian kernel produced the other fields
+            pk.all_reduce_finish(grp)
         v = pk.views
         return (v["dL_dmeans3D"], m2d, v.get("dL_dsh").view(P, M, 3) if M else None, v.get("dL_dcolors"),
                 v.get("dL_dfeature") if ctx.include else None, v["dL_dopacity"].view(ctx.opac_shape),

@@ -546,13 +546,15 @@ def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scale
 
 def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_feature, means3D, colors, language_feature, scales,
                                  rotations, scale_modifier, cov3D_precomp, sh, degree, include_feature, grads_depth=None,
-                                 debug=False, accumulate_into=None, means2D_per_view=None, accumulate=False):
+                                 debug=False, accumulate_into=None, means2D_per_view=None, accumulate=False, after_blend=None):
     """Backward of the V views rendered by rasterize_views_raw: every view's blend backward on its stream, then ONE
     per-Gaussian chain-rule kernel that sums over the views (mgs_backward_views).  Returns the 9-tuple of
     rasterize_gaussians_backward_raw holding the SUMS over the views (dL_dmeans2D: `means2D_per_view` [V,P,3] when given,
     else the sum).  `accumulate_into`: dict of preallocated fp32 tensors keyed like manigaussian_b200.parallel.FIELDS that
     receive the sums (e.g. the views of a PackedGradients buffer -- the all-reduce message); rows are overwritten unless
-    accumulate=True.  The caller's current stream holds the result on return."""
+    accumulate=True.  `after_blend()` is called between the blend stage and the per-Gaussian stage, when dL_dfeature is final
+    (multi-GPU: start its all-reduce there; it overlaps the per-Gaussian kernel).  The caller's current stream holds the
+    result on return."""
     L = _b.lib()
     dev = means3D.device
     P = means3D.size(0)
@@ -606,10 +608,14 @@ def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_featur
             w.dL_dmean2D = _ptr(m2d) if shared else _ptr(m2d[v])
             w.stream = streams[v].cuda_stream
             keep.append((bg, vm, pm, cp, gc, gf, gd, scratch))
-        _b.check(L.mgs_backward_views(V, arr, P, int(degree), M, F, _ptr(means3D), _ptr(sh) if M else None, _ptr(colors),
-                                      _ptr(language_feature) if F else None, _ptr(scales), float(scale_modifier), _ptr(rotations),
-                                      _ptr(cov3D_precomp), _ptr(dL_dmeans3D), _ptr(dL_dopacity), _ptr(dL_dcolors),
-                                      _ptr(dL_dfeature) if F else None, _ptr(dL_dcov3D), _ptr(dL_dsh) if M else None,
-                                      _ptr(dL_dscales) if has_sr else None, _ptr(dL_drotations) if has_sr else None,
-                                      int(shared), int(bool(accumulate)), int(bool(debug)), main.cuda_stream), "mgs_backward_views")
+        for stages in ((1, 2) if after_blend is not None else (3,)):
+            _b.check(L.mgs_backward_views(V, arr, P, int(degree), M, F, _ptr(means3D), _ptr(sh) if M else None, _ptr(colors),
+                                          _ptr(language_feature) if F else None, _ptr(scales), float(scale_modifier), _ptr(rotations),
+                                          _ptr(cov3D_precomp), _ptr(dL_dmeans3D), _ptr(dL_dopacity), _ptr(dL_dcolors),
+                                          _ptr(dL_dfeature) if F else None, _ptr(dL_dcov3D), _ptr(dL_dsh) if M else None,
+                                          _ptr(dL_dscales) if has_sr else None, _ptr(dL_drotations) if has_sr else None,
+                                          int(shared), int(bool(accumulate)), stages, int(bool(debug)), main.cuda_stream),
+                     "mgs_backward_views")
+            if stages == 1:
+                after_blend()
     return (m2d, dL_dcolors, dL_dfeature, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
