@@ -454,7 +454,72 @@ def make_e2e(impl_name, wl, torch, dist=None):
         state["dev"] = upload(Gh, Ch, Th)
         return compute(dev)
 
+    def graph_step_factory(Gh, Ch, Th):
+        """CUDA-graph variant (ours only): the whole step -- render_views forward, loss, backward -- is captured ONCE with
+        torch.cuda.graph (possible because nothing in it synchronises with the host or allocates outside torch's allocator;
+        the reference's forward blocks on a device->host copy of its instance count and cannot be captured) and replayed per
+        step.  Per step: one H2D copy of the packed inputs into the graph's static input buffer, one graph launch, one
+        asynchronous D2H copy of the loss."""
+        if not pack_state:
+            build_pack(Gh, Ch, Th)
+        from manigaussian_b200.gaussian_renderer import render_views
+        static = torch.empty_like(pack_state["packed"], device="cuda")
+        static.copy_(pack_state["packed"], non_blocking=True)
+        G = {k: v for k, v in Gh.items() if not (hasattr(v, "numel") and v.numel())}
+        C = [{k: v for k, v in ch.items() if not hasattr(v, "numel")} for ch in Ch]
+        T = [{k: None for k in th} for th in Th]
+        for (kind, i, k, v), o in zip(pack_state["fields"], pack_state["offs"]):
+            t = static[o:o + v.numel()].view(v.shape)
+            if kind == "G":
+                G[k] = t.requires_grad_(True)
+            elif kind == "C":
+                C[i][k] = t
+            else:
+                T[i][k] = t
+        views = [GaussianRasterizationSettings(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], cam["bg"], 1.0, cam["viewmatrix"],
+                                               cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, F > 0) for cam in C]
+        cc = torch.stack([ct["dL_dcolor"] for ct in T])
+        cf = torch.stack([ct["dL_dfeature"] for ct in T]) if F else None
+        cd = torch.stack([ct["dL_ddepth"] for ct in T]) if wl["depth"] else None
+
+        def fwd_bwd():
+            o = render_views(views, G["means3D"], G["rotations"], G["scales"], G["opacities"], features_color=G["shs"],
+                             features_language=G["feature"] if F else None, return_depth=wl["depth"], normalize_feature=False)
+            loss = (o["render"] * cc).sum()
+            if F:
+                loss = loss + (o["render_embed"] * cf).sum()
+            if wl["depth"]:
+                loss = loss + (o["depth"] * cd).sum()
+            loss.backward()
+            return loss
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):  # eager warm-up: learns the binning capacities, fills the allocator
+                for v in G.values():
+                    if getattr(v, "grad", None) is not None:
+                        v.grad = None
+                fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for v in G.values():
+            if getattr(v, "grad", None) is not None:
+                v.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = fwd_bwd()
+
+        def gstep(Gh_, Ch_, Th_, state):
+            static.copy_(pack_state["packed"], non_blocking=True)  # this step's inputs, pinned host -> the graph's input buffer
+            graph.replay()
+            return read_back(static_loss)
+        gstep.flush = flush
+        gstep.grads = lambda: {k: v.grad for k, v in G.items() if getattr(v, "grad", None) is not None}
+        return gstep
+
     step.flush = flush
+    step.graph_step_factory = graph_step_factory
     return step
 
 
@@ -752,6 +817,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-graph", action="store_true", help="also time the e2e step replayed from a CUDA graph (always done for small clouds)")
     ap.add_argument("--no-c5", action="store_true", help="skip the strong-scaling block (BASELINE configs[4]: 1M Gaussians, 8 views over the ranks)")
     ap.add_argument("--settle", type=float, default=1.5, help="seconds of untimed steps before the W warm-up steps "
                     "(lets clocks/power state and the caching allocator reach steady state)")
@@ -919,6 +985,26 @@ def main():
                        "copy stream), runs the public autograd API (ours: manigaussian_b200.gaussian_renderer.render_views, one node "
                        "for all views; reference: its autograd Function per view), and copies the loss to pinned host memory (async, value consumed one "
                        "step later, all K read before the clock stops)"}
+
+    if e2e is not None and a.impl == "ours" and world == 1 and (a.e2e_graph or P <= 100_000):
+        try:
+            gstep = step.graph_step_factory(Gh, Ch, Th)
+            gs = {}
+            for _ in range(max(3, a.warmup)):
+                gstep(Gh, Ch, Th, gs)
+            gstep.flush()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                gstep(Gh, Ch, Th, gs)
+            gstep.flush()
+            torch.cuda.synchronize()
+            tg = (time.perf_counter() - t0) / a.steps
+            e2e["cuda_graph"] = {"value": P * V / tg, "unit": "Gaussians/s", "ms_per_step": tg * 1e3,
+                                 "note": "same step, captured once with torch.cuda.graph and replayed: per step one H2D copy of the packed "
+                                         "inputs into the graph's input buffer, one graph launch, one async D2H of the loss"}
+        except Exception as ex:  # pragma: no cover
+            e2e["cuda_graph"] = {"error": repr(ex)[:300]}
 
     c5 = None
     if a.impl == "ours" and a.workload == "c3" and not a.no_c5:

@@ -235,6 +235,19 @@ typedef struct mgs_view {
 	char* blend_scratch;         /* backward: mgs_backward_scratch_bytes(P) */
 	float* dL_dmean2D;           /* backward output [P,3] or NULL */
 	void* stream;
+	/* Fused loss heads ("next" row f4; all NULL = off).  Forward: with target_color [3,H,W] the blend epilogue also produces
+	 * the L2 colour head of agents/manigaussian_bc/neural_rendering.py:300-308 (loss.py:12-13) and, with target_feature
+	 * [F,H,W], the cosine embedding head (:310-318, loss.py:18-23): loss_acc (device, 2 floats, zeroed by the call) receives
+	 * {sum (render - target)^2, sum_px cos_sim(embed, target)} -- loss_rgb = loss_acc[0] / (3 H W), loss_embed =
+	 * 1 - loss_acc[1] / (H W) -- and cot_color [3,H,W] / cot_feature [F,H,W] receive d loss_rgb / d render and
+	 * d loss_embed / d embed.  Backward: pass those planes as dL_dpix / dL_dpix_F; cot_scale (device, 2 floats, or NULL for 1)
+	 * holds the upstream gradients of the two scalar losses and multiplies the planes on load. */
+	const float* target_color;
+	const float* target_feature;
+	float* cot_color;
+	float* cot_feature;
+	float* loss_acc;
+	const float* cot_scale;
 } mgs_view;
 
 int mgs_forward_views(
@@ -276,6 +289,11 @@ int mgs_backward_views(
 	int stages,            /* 1: blend stage of every view (dL_dfeature is final afterwards), 2: the per-Gaussian stage, 3: both */
 	int debug,
 	void* join_stream);
+
+/* The same two loss heads for V images that already sit in device memory (planar color [V,3,N], feature [V,F,N] or NULL,
+ * N = H*W): loss_acc [V,2] (zeroed by the call) and the cotangent planes as above, one launch. */
+int mgs_loss_heads(int V, int F, int N, const float* color, const float* feature, const float* target_color,
+	const float* target_feature, float* cot_color, float* cot_feature, float* loss_acc, void* stream);
 
 /* Frustum test.  Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29, rasterizer_impl.cu:141-153).
  * present: uint8 [P], 1 where view-space z > 0.2. */

@@ -22,7 +22,9 @@ class View(C.Structure):
                 ("out_color", C.c_void_p), ("out_feature", C.c_void_p), ("out_depth", C.c_void_p), ("radii", C.c_void_p),
                 ("status", C.c_void_p),
                 ("dL_dpix", C.c_void_p), ("dL_dpix_F", C.c_void_p), ("dL_dpix_depth", C.c_void_p),
-                ("blend_scratch", C.c_void_p), ("dL_dmean2D", C.c_void_p), ("stream", C.c_void_p)]
+                ("blend_scratch", C.c_void_p), ("dL_dmean2D", C.c_void_p), ("stream", C.c_void_p),
+                ("target_color", C.c_void_p), ("target_feature", C.c_void_p), ("cot_color", C.c_void_p),
+                ("cot_feature", C.c_void_p), ("loss_acc", C.c_void_p), ("cot_scale", C.c_void_p)]
 
 
 _lib = None
@@ -81,6 +83,8 @@ def lib():
                                      vp, f, vp, vp,                     # scales scale_modifier rotations cov3D_precomp
                                      vp, vp, vp, vp, vp, vp, vp, vp,    # dL: mean3D opacity color feature cov3D sh scale rot
                                      i, i, i, i, vp]                    # shared_mean2D accumulate stages debug join_stream
+    L.mgs_loss_heads.restype = C.c_int
+    L.mgs_loss_heads.argtypes = [i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.mgs_mark_visible.restype = C.c_int
     L.mgs_mark_visible.argtypes = [i, vp, vp, vp, vp, vp]
     L.mgs_state_array.restype = C.c_int
@@ -108,7 +112,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "mgs_abi_version", "mgs_last_error", "mgs_geometry_state_bytes", "mgs_image_state_bytes",
     "mgs_binning_state_bytes", "mgs_backward_scratch_bytes", "mgs_forward", "mgs_forward_begin", "mgs_forward_finish",
-    "mgs_backward", "mgs_forward_views", "mgs_backward_views",
+    "mgs_backward", "mgs_forward_views", "mgs_backward_views", "mgs_loss_heads",
     "mgs_activate", "mgs_activate_backward",
     "mgs_mark_visible", "mgs_state_array", "mgs_profile_enable", "mgs_profile_num_stages",
     "mgs_profile_stage_name", "mgs_profile_read",

@@ -579,6 +579,13 @@ int mgs_forward_views(
 				ba.want_depth = w.out_depth != nullptr;
 				ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
 				ba.out_color = w.out_color; ba.out_feature = w.out_feature; ba.out_depth = w.out_depth;
+				if (w.target_color) {
+					if (!w.cot_color || !w.loss_acc || (w.target_feature && Fv > 0 && !w.cot_feature))
+						return fail(MGS_ERR_INVALID_ARG, "view: loss heads need cot_color, loss_acc (and cot_feature with target_feature)");
+					ba.tgt_color = w.target_color; ba.tgt_feature = Fv > 0 ? w.target_feature : nullptr;
+					ba.cot_color = w.cot_color; ba.cot_feature = w.cot_feature; ba.loss_acc = w.loss_acc;
+					MGS_CUDA(cudaMemsetAsync(w.loss_acc, 0, 2 * sizeof(float), st));
+				}
 				{ StageTimer t_(ST_BLEND_FWD, st); launch_blend_fwd(ba, st); }
 				MGS_STAGE("blend_fwd");
 			}
@@ -641,6 +648,7 @@ int mgs_backward_views(
 		ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
 		ba.dL_dcolor = w.dL_dpix; ba.dL_dfeature = F > 0 ? w.dL_dpix_F : nullptr; ba.dL_ddepth = w.dL_dpix_depth;
 		ba.gb = gb; ba.dL_dfeat = F > 0 ? dL_dfeature : nullptr;
+		ba.cot_scale = w.cot_scale;
 		if (w.binning_capacity > 0) {
 			{ StageTimer t_(ST_BLEND_BWD, st); launch_blend_bwd(ba, st); }
 			MGS_STAGE("blend_bwd");
@@ -684,6 +692,22 @@ int mgs_backward_views(
 		{ StageTimer t_(ST_PROJECT_BWD, st); launch_project_bwd_views(pb, st); }
 		MGS_STAGE("project_bwd");
 	}
+	return 0;
+}
+
+int mgs_loss_heads(int V, int F, int N, const float* color, const float* feature, const float* target_color,
+	const float* target_feature, float* cot_color, float* cot_feature, float* loss_acc, void* stream)
+{
+	if (V <= 0 || N <= 0 || F < 0) return fail(MGS_ERR_INVALID_ARG, "bad V/N/F");
+	if (!color || !target_color || !cot_color || !loss_acc) return fail(MGS_ERR_INVALID_ARG, "color, target_color, cot_color and loss_acc are required");
+	const bool emb = F > 0 && feature && target_feature;
+	if (emb && !cot_feature) return fail(MGS_ERR_INVALID_ARG, "cot_feature is required with features");
+	cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+	MGS_CUDA(cudaMemsetAsync(loss_acc, 0, (size_t)V * 2 * sizeof(float), st));
+	launch_loss_heads(V, emb ? F : 0, N, color, emb ? feature : nullptr, target_color, emb ? target_feature : nullptr, cot_color, cot_feature,
+		loss_acc, st);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(MGS_ERR_CUDA, std::string("loss_heads: ") + cudaGetErrorString(e));
 	return 0;
 }
 

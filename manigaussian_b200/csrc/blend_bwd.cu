@@ -95,11 +95,13 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 	float T = 0.f, bgterm = 0.f;
 	{
 		float g4[4] = { 0.f, 0.f, 0.f, 0.f };
+		// upstream gradients of the fused loss heads (loss_heads.cuh): the cotangent planes were written for d loss = 1
+		const float sc_color = a.cot_scale ? a.cot_scale[0] : 1.f, sc_feat = a.cot_scale ? a.cot_scale[1] : 1.f;
 		if (inside) {
 			nc = a.n_contrib[pix];
 			T = a.final_T[pix];
 #pragma unroll
-			for (int ch = 0; ch < 3; ch++) g4[ch] = a.dL_dcolor[ch * HW + pix];
+			for (int ch = 0; ch < 3; ch++) g4[ch] = sc_color * a.dL_dcolor[ch * HW + pix];
 			if (a.dL_ddepth) g4[3] = a.dL_ddepth[pix];
 		}
 		bgterm = T * (a.bg[0] * g4[0] + a.bg[1] * g4[1] + a.bg[2] * g4[2]);
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 		if (NFT > 0) {
 #pragma unroll
 			for (int i = 0; i < 8 * NFT; i++)
-				grow[2 * i] = (inside && i < F && a.dL_dfeature) ? a.dL_dfeature[(size_t)i * HW + pix] : 0.f;
+				grow[2 * i] = (inside && i < F && a.dL_dfeature) ? sc_feat * a.dL_dfeature[(size_t)i * HW + pix] : 0.f;
 		}
 	}
 	uint32_t maxc = nc;

@@ -25,6 +25,7 @@
 //    with x = gid the output planes are written as full 32-byte sectors straight from the D fragments.
 #include "blend_common.cuh"
 #include "blend_mma.cuh"
+#include "loss_heads.cuh"
 
 namespace mgs {
 
@@ -255,31 +256,88 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 	s_w[lane] = T;
 	__syncwarp();
 	const int ox = bx0 + gid;  // fragment role: this thread holds pixels (x = gid, y = 0..3)
-	if (ox < a.W) {
+	const bool heads = a.tgt_color != nullptr;              // fused loss heads (loss_heads.cuh)
+	const bool embed = heads && NFT > 0 && a.tgt_feature != nullptr;
+	const float invN = 1.0f / (float)HW;
+	float s_rgb = 0.f, s_cos = 0.f;                         // this thread's share of the two loss sums
 #pragma unroll
-		for (int mt = 0; mt < 2; mt++) {
+	for (int mt = 0; mt < 2; mt++) {
 #pragma unroll
-			for (int h = 0; h < 2; h++) {
-				const int y = 2 * mt + h, oy = by0 + y;
-				if (oy >= a.H) continue;
-				const size_t pix = (size_t)a.W * oy + ox;
-				const float Tp = s_w[4 * gid + y];
+		for (int h = 0; h < 2; h++) {
+			const int y = 2 * mt + h, oy = by0 + y;
+			const bool in = ox < a.W && oy < a.H;
+			const size_t pix = in ? (size_t)a.W * oy + ox : 0;
+			const float Tp = s_w[4 * gid + y];
 #pragma unroll
-				for (int nt = 0; nt < NFT; nt++) {
-#pragma unroll
-					for (int e = 0; e < 2; e++) {
-						const int f = 8 * nt + 2 * tig + e;
-						if (f < F) a.out_feature[(size_t)f * HW + pix] = acc[mt][nt][2 * h + e];
-					}
-				}
+			for (int nt = 0; nt < NFT; nt++) {
 #pragma unroll
 				for (int e = 0; e < 2; e++) {
-					const int c = 2 * tig + e;  // column of the {r,g,b,depth} tile
-					const float v = acc[mt][NFT][2 * h + e];
-					if (c < 3) a.out_color[(size_t)c * HW + pix] = v + Tp * a.bg[c];
-					else if (c == 3 && a.out_depth) a.out_depth[pix] = v;
+					const int f = 8 * nt + 2 * tig + e;
+					if (in && f < F) a.out_feature[(size_t)f * HW + pix] = acc[mt][nt][2 * h + e];
 				}
 			}
+			float col[2];
+#pragma unroll
+			for (int e = 0; e < 2; e++) {
+				const int c = 2 * tig + e;  // column of the {r,g,b,depth} tile
+				col[e] = acc[mt][NFT][2 * h + e] + (c < 3 ? Tp * a.bg[c] : 0.f);
+				if (in && c < 3) a.out_color[(size_t)c * HW + pix] = col[e];
+				else if (in && c == 3 && a.out_depth) a.out_depth[pix] = col[e];
+			}
+			if (heads) {  // warp-uniform
+#pragma unroll
+				for (int e = 0; e < 2; e++) {
+					const int c = 2 * tig + e;
+					if (in && c < 3) {
+						const float d = col[e] - a.tgt_color[(size_t)c * HW + pix];
+						s_rgb += d * d;
+						a.cot_color[(size_t)c * HW + pix] = (2.0f / 3.0f) * invN * d;
+					}
+				}
+				if (embed) {
+					// this thread holds 2 NFT of the pixel's features; the other three threads of the quad hold the rest
+					float tg[NFT > 0 ? NFT : 1][2];
+					float xy = 0.f, xx = 0.f, yy = 0.f;
+#pragma unroll
+					for (int nt = 0; nt < NFT; nt++) {
+#pragma unroll
+						for (int e = 0; e < 2; e++) {
+							const int f = 8 * nt + 2 * tig + e;
+							const float x = acc[mt][nt][2 * h + e];
+							const float g = (in && f < F) ? a.tgt_feature[(size_t)f * HW + pix] : 0.f;
+							tg[nt][e] = g;
+							xy += x * g; xx += x * x; yy += g * g;
+						}
+					}
+#pragma unroll
+					for (int o = 1; o <= 2; o <<= 1) {
+						xy += __shfl_xor_sync(0xffffffffu, xy, o);
+						xx += __shfl_xor_sync(0xffffffffu, xx, o);
+						yy += __shfl_xor_sync(0xffffffffu, yy, o);
+					}
+					const CosTerms ct = cos_terms(xy, xx, yy);
+					if (in && tig == 0) s_cos += ct.cos;
+#pragma unroll
+					for (int nt = 0; nt < NFT; nt++) {
+#pragma unroll
+						for (int e = 0; e < 2; e++) {
+							const int f = 8 * nt + 2 * tig + e;
+							if (in && f < F) a.cot_feature[(size_t)f * HW + pix] = -invN * cos_grad(ct, acc[mt][nt][2 * h + e], tg[nt][e]);
+						}
+					}
+				}
+			}
+		}
+	}
+	if (heads) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			s_rgb += __shfl_xor_sync(0xffffffffu, s_rgb, o);
+			s_cos += __shfl_xor_sync(0xffffffffu, s_cos, o);
+		}
+		if (lane == 0) {
+			red_add(a.loss_acc, s_rgb);
+			if (embed) red_add(a.loss_acc + 1, s_cos);
 		}
 	}
 }

@@ -93,7 +93,20 @@ struct BlendArgs {
 	const float* dL_ddepth;      // [H,W] nullable
 	float* gb;                   // [P,GB_STRIDE] (zeroed by caller)
 	float* dL_dfeat;             // [P,F] (zeroed by caller) nullable
+	// fused loss heads (loss_heads.cuh), all nullable.  Forward: with tgt_color the epilogue also writes the cotangent planes
+	// cot_color [3,H,W] (and, with tgt_feature, cot_feature [F,H,W]) and adds {sum (x-g)^2, sum_px cos} into loss_acc[0..1].
+	// Backward: cot_scale[0..1] (device) multiply the colour / feature cotangent planes on load (the upstream gradients of
+	// the two scalar losses).
+	const float* tgt_color;
+	const float* tgt_feature;
+	float* cot_color;
+	float* cot_feature;
+	float* loss_acc;
+	const float* cot_scale;
 };
+// loss_heads.cu: the same heads for images that already sit in memory (planar [3,H,W] / [F,H,W], V views in one launch)
+void launch_loss_heads(int V, int F, int N, const float* color, const float* feature, const float* tgt_color, const float* tgt_feature,
+	float* cot_color, float* cot_feature, float* loss_acc, cudaStream_t s);
 
 // activate.cu: view-independent per-Gaussian pre-ops (activations, deformation offsets, feature normalisation)
 struct ActivateArgs {

@@ -172,8 +172,84 @@ class _RasterizeViews(torch.autograd.Function):
                 v["dL_dscales"], v["dL_drotations"], None, None, None)
 
 
+class _RasterizeViewsLoss(torch.autograd.Function):
+    """render_views with the loss heads fused into the forward blend's epilogue: returns the per-view
+    L2 colour loss and cosine embedding loss of NeuralRenderer.forward (neural_rendering.py:300-318, loss.py:12-23); the
+    images come back too, but gradients flow through the two losses only."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, feature, opacities, scales, rotations, views, target_rgb, target_embed, group):
+        dev = means3D.device
+        V, P = len(views), means3D.shape[0]
+        H, W = int(views[0].image_height), int(views[0].image_width)
+        if any((int(s.image_height), int(s.image_width)) != (H, W) for s in views):
+            raise ValueError("render_views needs one image size for all views")
+        include = feature is not None and feature.numel() > 0
+        F = int(feature.shape[1]) if include else 0
+        means3D, sh, colors_precomp, feature = (_prep(t, dev) for t in (means3D, sh, colors_precomp, feature))
+        opacities, scales, rotations = (_prep(t, dev) for t in (opacities, scales, rotations))
+        target_rgb = _prep(target_rgb, dev)
+        target_embed = _prep(target_embed, dev) if (include and target_embed is not None) else None
+        if tuple(target_rgb.shape) != (V, 3, H, W) or (target_embed is not None and tuple(target_embed.shape) != (V, F, H, W)):
+            raise ValueError("targets must be [V,3,H,W] and [V,F,H,W]")
+        opts = dict(dtype=torch.float32, device=dev)
+        color = torch.empty((V, 3, H, W), **opts)
+        feat_img = torch.empty((V, F, H, W), **opts) if include else None
+        cot_rgb = torch.empty((V, 3, H, W), **opts)
+        cot_embed = torch.empty((V, F, H, W), **opts) if target_embed is not None else (torch.zeros((V, F, H, W), **opts) if include else None)
+        loss_acc = torch.empty((V, 2), **opts)
+        degree = views[0].sh_degree
+        outs, streams = rasterize_views_raw(views, means3D, colors_precomp, feature, opacities, scales, rotations,
+                                            views[0].scale_modifier, None, sh, degree, include, debug=views[0].debug,
+                                            out_buffers=(color, feat_img, None),
+                                            loss_heads=(target_rgb, target_embed, cot_rgb, cot_embed, loss_acc))
+        N = float(H * W)
+        loss_rgb = loss_acc[:, 0] / (3.0 * N)
+        loss_embed = 1.0 - loss_acc[:, 1] / N if target_embed is not None else torch.zeros((V,), **opts)
+        radii = torch.stack([o[3] for o in outs])
+        ctx.views, ctx.streams, ctx.group = views, streams, group
+        ctx.outs = outs
+        ctx.include, ctx.F, ctx.degree = include, F, degree
+        ctx.opac_shape = opacities.shape
+        ctx.cots = (cot_rgb, cot_embed)
+        ctx.save_for_backward(means3D, sh if sh is not None else torch.empty(0, device=dev),
+                              colors_precomp if colors_precomp is not None else torch.empty(0, device=dev),
+                              feature if include else torch.empty(0, device=dev), scales, rotations)
+        ctx.mark_non_differentiable(radii, color)
+        empty = torch.empty(0, device=dev)
+        if include:
+            ctx.mark_non_differentiable(feat_img)
+        return loss_rgb, loss_embed, color, (feat_img if include else empty), radii
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_embed, _gc, _gf, _gr):
+        means3D, sh, colors_precomp, feature, scales, rotations = ctx.saved_tensors
+        dev = means3D.device
+        views, V, P = ctx.views, len(ctx.views), means3D.shape[0]
+        M = sh.shape[1] if sh.numel() else 0
+        use_colors = colors_precomp.numel() > 0
+        z = torch.zeros((V,), dtype=torch.float32, device=dev)
+        scale = torch.stack([g_rgb if g_rgb is not None else z, g_embed if g_embed is not None else z], 1).contiguous()
+        cot_rgb, cot_embed = ctx.cots
+        pk = PackedGradients(P, ctx.F, M, dev, colors=use_colors, zero=False)
+        grp = None if ctx.group in (None, True) else ctx.group
+        m2d = torch.empty((V, P, 3), dtype=torch.float32, device=dev)
+        rasterize_views_backward_raw(views, ctx.outs, ctx.streams, cot_rgb, cot_embed if ctx.include else None, means3D,
+                                     colors_precomp if use_colors else None, feature if ctx.include else None, scales, rotations,
+                                     views[0].scale_modifier, None, sh if M else None, ctx.degree, ctx.include, debug=views[0].debug,
+                                     accumulate_into=pk.views, means2D_per_view=m2d, cot_scale=scale,
+                                     after_blend=(lambda: pk.all_reduce_begin(grp)) if ctx.group is not None else None)
+        if ctx.group is not None:
+            pk.all_reduce_finish(grp)
+        v = pk.views
+        return (v["dL_dmeans3D"], m2d, v.get("dL_dsh").view(P, M, 3) if M else None, v.get("dL_dcolors"),
+                v.get("dL_dfeature") if ctx.include else None, v["dL_dopacity"].view(ctx.opac_shape),
+                v["dL_dscales"], v["dL_drotations"], None, None, None, None)
+
+
 def render_views(cameras, pts_xyz, rotations, scales, opacity, bg_color=(0.0, 0.0, 0.0), pts_rgb=None, features_color=None,
-                 features_language=None, view_ids=None, return_depth=False, sync_gradients=None, normalize_feature=True):
+                 features_language=None, view_ids=None, return_depth=False, sync_gradients=None, normalize_feature=True,
+                 targets=None):
     """Render several cameras of one Gaussian cloud in one autograd node.
 
     cameras: `cameras.CameraBatch` (or a sequence of GaussianRasterizationSettings); view_ids selects a subset (e.g. this
@@ -181,6 +257,10 @@ def render_views(cameras, pts_xyz, rotations, scales, opacity, bg_color=(0.0, 0.
     (all-reduce over the default process group) or a process group -- the per-Gaussian gradients of this rank's views are
     then summed over ranks inside the backward with one collective.  normalize_feature=False skips the reference's
     per-render feature normalisation (for callers that already hold unit features, e.g. `activate_gaussians` output).
+    targets: {"rgb": [V,3,H,W], "embed": [V,F,H,W] (optional)} fuses ManiGaussian's loss heads into the forward blend's
+    epilogue: the result then also holds "loss_rgb" and "loss_embed" ([V] each: l2_loss and cosine_loss of
+    agents/manigaussian_bc/loss.py per view; combine them as neural_rendering.py:300-318 does) through which -- and only
+    through which -- gradients flow; "render"/"render_embed" are returned detached.
     Returns {"render" [V,3,H,W], "render_embed" [V,F,H,W] | None, "depth" [V,H,W] (if asked), "viewspace_points" [V,P,3]
     (its .grad holds each view's screen-space mean gradients), "radii" [V,P] int32}."""
     device = pts_xyz.device
@@ -201,6 +281,14 @@ def render_views(cameras, pts_xyz, rotations, scales, opacity, bg_color=(0.0, 0.
         feat = normalize_features(features_language) if normalize_feature else features_language
     V, P = len(views), pts_xyz.shape[0]
     screenspace_points = torch.zeros((V, P, 3), dtype=torch.float32, device=device, requires_grad=True)
+    if targets is not None:
+        if return_depth:
+            raise ValueError("targets and return_depth cannot be combined")
+        loss_rgb, loss_embed, color, feat_img, radii = _RasterizeViewsLoss.apply(
+            pts_xyz, screenspace_points, features_color, pts_rgb if features_color is None else None, feat, opacity, scales,
+            rotations, views, targets["rgb"], targets.get("embed"), sync_gradients)
+        return {"render": color, "render_embed": feat_img if include else None, "viewspace_points": screenspace_points,
+                "radii": radii, "loss_rgb": loss_rgb, "loss_embed": loss_embed}
     if V == 1 and sync_gradients is None:
         # a single view needs neither side streams nor the packed accumulation buffer: the single-view operator is leaner
         out = GaussianRasterizer(views[0], return_depth=return_depth)(

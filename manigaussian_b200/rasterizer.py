@@ -378,6 +378,19 @@ _VIEW_STREAMS = {}
 _CAPACITY = {}        # (device index, P, W, H, slot) -> instance capacity to use for the next call
 _PENDING_STATUS = []  # [(key, pinned int32[2], cuda event, capacity used)] of forwards whose status has not been read yet
 _SIZES = {}
+_STATUS_RING = {"buf": None, "next": 0}   # pinned {count, overflow} slots, handed out round-robin (pin_memory() per call would
+_STATUS_SLOTS = 4096                       # cost a cudaHostAlloc and a device synchronisation each time)
+
+
+def _status_slots(n):
+    """n consecutive pinned int32[2] slots.  A slot is reused after _STATUS_SLOTS later views: by then its forward finished."""
+    if _STATUS_RING["buf"] is None:
+        _STATUS_RING["buf"] = torch.zeros((_STATUS_SLOTS, 2), dtype=torch.int32).pin_memory()
+    i = _STATUS_RING["next"]
+    if i + n > _STATUS_SLOTS:
+        i = 0
+    _STATUS_RING["next"] = i + n
+    return _STATUS_RING["buf"][i:i + n]
 
 
 def _view_streams(device, n):
@@ -411,8 +424,10 @@ def _poll_status(block=False):
                           f"{R - cap} instances were dropped from that render (capacity raised for the next call)")
             want = _round_capacity(R * 1.5 + 4096)
         cur = _CAPACITY.get(key, 0)
-        # grow at once, shrink slowly (a render with few instances must not starve the next one)
-        _CAPACITY[key] = want if want > cur else max(want, int(cur * 0.98))
+        # grow at once; shrink only when the state is more than twice too large (stable sizes keep hitting the same cached
+        # allocation, and a render with few instances must not starve the next one)
+        if want > cur or want < cur // 2:
+            _CAPACITY[key] = want
     _PENDING_STATUS[:] = keep
 
 
@@ -473,13 +488,17 @@ def _calibrate(L, views, keys, dev, P, degree, M, means3D, sh, colors, opacity, 
 
 
 def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scales, rotations, scale_modifier, cov3D_precomp,
-                        sh, degree, include_feature, return_depth=False, debug=False, out_buffers=None, capacities=None):
+                        sh, degree, include_feature, return_depth=False, debug=False, out_buffers=None, capacities=None,
+                        loss_heads=None):
     """Forward of V views of one Gaussian cloud.  `views` is a sequence of GaussianRasterizationSettings (bg, viewmatrix,
     projmatrix, tanfov*, image size, campos are read per view).  Returns (outs, streams): outs[v] is a ViewOut; all work
     is joined into the caller's current stream before the call returns (`streams` are the per-view streams used).
     `out_buffers` = (color [V,3,H,W], feature [V,F,H,W] or None, depth [V,H,W] or None): render straight into slices of
     caller-owned batch tensors instead of per-view allocations.  `capacities` (per-view instance capacities) overrides
-    the history-based sizing of the binning state."""
+    the history-based sizing of the binning state.  `loss_heads` = (target_rgb [V,3,H,W], target_embed [V,F,H,W] or None,
+    cot_rgb [V,3,H,W], cot_embed [V,F,H,W] or None, loss_acc [V,2]): the forward blend's epilogue also evaluates the L2 colour
+    head and the cosine embedding head against the targets (C ABI mgs_view.target_*), leaving the loss sums in loss_acc and
+    the cotangent planes ready for rasterize_views_backward_raw."""
     L = _b.lib()
     dev = means3D.device
     if not means3D.is_cuda:
@@ -496,13 +515,18 @@ def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scale
     streams = _view_streams(dev, V) if V > 1 else [main]  # a single view needs no side stream
     di = dev.index if dev.index is not None else torch.cuda.current_device()
     keys = [(di, P, int(s.image_width), int(s.image_height), v) for v, s in enumerate(views)]
+    capturing = torch.cuda.is_current_stream_capturing()  # inside a CUDA-graph capture: no event queries, no calibration
     with torch.cuda.device(dev):
-        _poll_status()
+        if not capturing:
+            _poll_status()
         if capacities is None and any(k not in _CAPACITY for k in keys):
+            if capturing:
+                raise RuntimeError("render the views once before capturing them in a CUDA graph (the binning capacity is learned "
+                                   "from an eager call) or pass `capacities`")
             _calibrate(L, views, keys, dev, P, degree, M, means3D, sh, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                        debug)
         arr = (_b.View * V)()
-        status = torch.zeros((V, 2), dtype=torch.int32).pin_memory()
+        status = _status_slots(V)
         keep, outs = [], []
         for v, s in enumerate(views):
             H, W = int(s.image_height), int(s.image_width)
@@ -529,6 +553,11 @@ def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scale
             w.out_color, w.out_feature, w.out_depth, w.radii = _ptr(out_color), (_ptr(out_feature) if F else None), _ptr(out_depth), _ptr(radii)
             w.status = status.data_ptr() + 8 * v
             w.stream = streams[v].cuda_stream
+            if loss_heads is not None:
+                t_rgb, t_emb, c_rgb, c_emb, l_acc = loss_heads
+                w.target_color, w.cot_color, w.loss_acc = _ptr(t_rgb[v]), _ptr(c_rgb[v]), _ptr(l_acc[v])
+                if t_emb is not None and F:
+                    w.target_feature, w.cot_feature = _ptr(t_emb[v]), _ptr(c_emb[v])
             keep.append((bg, vm, pm, cp))
             ret = (cap, out_color, out_feature, radii, geom, binb, img) + ((out_depth,) if return_depth else ())
             outs.append(ViewOut(ret))
@@ -539,22 +568,24 @@ def rasterize_views_raw(views, means3D, colors, language_feature, opacity, scale
         ev.record(main)
         for v, o in enumerate(outs):
             o.status, o.event = status[v], ev
-            if capacities is None:
+            if capacities is None and not capturing:
                 _PENDING_STATUS.append((keys[v], status[v], ev, o[0]))
     return outs, streams
 
 
 def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_feature, means3D, colors, language_feature, scales,
                                  rotations, scale_modifier, cov3D_precomp, sh, degree, include_feature, grads_depth=None,
-                                 debug=False, accumulate_into=None, means2D_per_view=None, accumulate=False, after_blend=None):
+                                 debug=False, accumulate_into=None, means2D_per_view=None, accumulate=False, after_blend=None,
+                                 cot_scale=None):
     """Backward of the V views rendered by rasterize_views_raw: every view's blend backward on its stream, then ONE
     per-Gaussian chain-rule kernel that sums over the views (mgs_backward_views).  Returns the 9-tuple of
     rasterize_gaussians_backward_raw holding the SUMS over the views (dL_dmeans2D: `means2D_per_view` [V,P,3] when given,
     else the sum).  `accumulate_into`: dict of preallocated fp32 tensors keyed like manigaussian_b200.parallel.FIELDS that
     receive the sums (e.g. the views of a PackedGradients buffer -- the all-reduce message); rows are overwritten unless
     accumulate=True.  `after_blend()` is called between the blend stage and the per-Gaussian stage, when dL_dfeature is final
-    (multi-GPU: start its all-reduce there; it overlaps the per-Gaussian kernel).  The caller's current stream holds the
-    result on return."""
+    (multi-GPU: start its all-reduce there; it overlaps the per-Gaussian kernel).  `cot_scale` [V,2] (device): upstream
+    gradients of the fused loss heads' two scalars per view, multiplied onto the colour / feature cotangent planes as they
+    are loaded.  The caller's current stream holds the result on return."""
     L = _b.lib()
     dev = means3D.device
     P = means3D.size(0)
@@ -607,6 +638,8 @@ def rasterize_views_backward_raw(views, outs, streams, grads_color, grads_featur
             w.blend_scratch = scratch.data_ptr()
             w.dL_dmean2D = _ptr(m2d) if shared else _ptr(m2d[v])
             w.stream = streams[v].cuda_stream
+            if cot_scale is not None:
+                w.cot_scale = cot_scale.data_ptr() + 8 * v
             keep.append((bg, vm, pm, cp, gc, gf, gd, scratch))
         for stages in ((1, 2) if after_blend is not None else (3,)):
             _b.check(L.mgs_backward_views(V, arr, P, int(degree), M, F, _ptr(means3D), _ptr(sh) if M else None, _ptr(colors),

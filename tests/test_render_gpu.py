@@ -255,3 +255,124 @@ def test_dyna_step_end_to_end_gradients():
     for k in ("xyz_maps", "rot_maps", "scale_maps", "opacity_maps", "sh", "feature_maps", "next_xyz", "next_rot"):
         assert a[k].grad is not None, k
         assert util.rel_l2(a[k].grad.cpu().numpy(), b[k].grad.cpu().numpy()) < 2e-5, k
+
+
+def test_step_is_cuda_graph_capturable():
+    """The multi-view step never synchronises with the host and allocates only through torch's allocator, so forward +
+    loss + backward can be captured ONCE with torch.cuda.graph and replayed (the reference's forward blocks on a device->host
+    copy of its instance count, rasterizer_impl.cu:284, and cannot).  Replays must reproduce the eager gradients, also after
+    the inputs changed in place."""
+    import torch
+    from manigaussian_b200.gaussian_renderer import render_views
+    P, F, W, H, V = 12000, 32, 80, 64, 3
+    g = _cloud(P, F, 29)
+    cams = _cams(V, W, H)
+    names = ("means3D", "rotations", "scales", "opacities", "shs", "feature")
+    L = {k: _t(np.asarray(g[k], np.float32)).requires_grad_(True) for k in names}
+    cts = (torch.randn(V, 3, H, W, device="cuda"), torch.randn(V, F, H, W, device="cuda"))
+
+    def fwd_bwd():
+        o = render_views(cams, L["means3D"], L["rotations"], L["scales"], L["opacities"], features_color=L["shs"],
+                         features_language=L["feature"])
+        loss = (o["render"] * cts[0]).sum() + (o["render_embed"] * cts[1]).sum()
+        loss.backward()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            for v in L.values():
+                v.grad = None
+            fwd_bwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    eager = {k: v.grad.clone() for k, v in L.items()}
+    for v in L.values():
+        v.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss = fwd_bwd()
+    for rep in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    for k in names:
+        assert util.rel_l2(L[k].grad.cpu().numpy(), eager[k].cpu().numpy()) < 1e-5, k
+    # new input values in the same buffers: the replay must follow them
+    with torch.no_grad():
+        L["means3D"].add_(0.01)
+    graph.replay()
+    torch.cuda.synchronize()
+    moved = {k: v.grad.clone() for k, v in L.items()}
+    for v in L.values():
+        v.grad = None
+    fwd_bwd()
+    torch.cuda.synchronize()
+    for k in names:
+        assert util.rel_l2(moved[k].cpu().numpy(), L[k].grad.cpu().numpy()) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", ["f32", "f3"])
+def test_loss_heads_kernel_matches_reference_golden(name):
+    """mgs_loss_heads (the device code the forward blend's epilogue shares, loss_heads.cuh) on the golden images produced
+    with the REFERENCE's own l2_loss / cosine_loss (tests/golden/make_loss_golden.py): loss values and both cotangent planes."""
+    import torch
+    from manigaussian_b200 import _binding as b
+    z = np.load(os.path.join(GOLD, "loss_heads.npz"))
+    render, gt, embed, gt_e = (_t(z[f"{name}_{k}"])[None].contiguous() for k in ("render", "gt", "embed", "gt_embed"))
+    F, H, W = embed.shape[1:]
+    cot_c, cot_f = torch.empty_like(render), torch.empty_like(embed)
+    acc = torch.empty((1, 2), device="cuda")
+    b.check(b.lib().mgs_loss_heads(1, F, H * W, render.data_ptr(), embed.data_ptr(), gt.data_ptr(), gt_e.data_ptr(), cot_c.data_ptr(),
+                                   cot_f.data_ptr(), acc.data_ptr(), torch.cuda.current_stream().cuda_stream), "mgs_loss_heads")
+    torch.cuda.synchronize()
+    loss_rgb = float(acc[0, 0]) / (3 * H * W)
+    loss_embed = 1.0 - float(acc[0, 1]) / (H * W)
+    assert abs(loss_rgb - float(z[f"{name}_loss_rgb"])) <= 2e-6 * abs(float(z[f"{name}_loss_rgb"]))
+    assert abs(loss_embed - float(z[f"{name}_loss_embed"])) <= 2e-6
+    assert util.rel_l2(cot_c[0].cpu().numpy(), z[f"{name}_d_render"]) < 2e-6
+    assert util.rel_l2(cot_f[0].cpu().numpy(), z[f"{name}_d_embed"]) < 1e-5
+
+
+@pytest.mark.parametrize("F,lam", [(32, 0.01), (3, 1.0), (0, 0.0)])
+def test_loss_heads_fused_into_the_blend_epilogue(F, lam):
+    """render_views(targets=...) -- the L2 colour head and the cosine embedding head evaluated in the forward blend's
+    epilogue, their cotangents consumed by the backward blend -- against the same objective built from the reference's
+    PyTorch expressions (loss.py:12-23 as combined in neural_rendering.py:300-318) on the unfused render."""
+    import torch
+    from manigaussian_b200.gaussian_renderer import render_views
+    P, W, H, V = 9000, 72, 56, 3
+    g = _cloud(P, max(F, 1), 37)
+    cams = _cams(V, W, H)
+    names = ("means3D", "rotations", "scales", "opacities", "shs") + (("feature",) if F else ())
+    tgt_rgb = torch.rand(V, 3, H, W, device="cuda")
+    tgt_emb = torch.randn(V, F, H, W, device="cuda") if F else None
+
+    def leaves():
+        d = {k: _t(np.asarray(g[k], np.float32)).requires_grad_(True) for k in names}
+        if F and F != g["feature"].shape[1]:
+            d["feature"] = _t(np.asarray(g["feature"][:, :F], np.float32)).requires_grad_(True)
+        return d
+
+    a = leaves()
+    o = render_views(cams, a["means3D"], a["rotations"], a["scales"], a["opacities"], features_color=a["shs"],
+                     features_language=a.get("feature"), targets={"rgb": tgt_rgb, "embed": tgt_emb})
+    loss_a = o["loss_rgb"].sum() + lam * o["loss_embed"].sum()
+    loss_a.backward()
+
+    b = leaves()
+    r = render_views(cams, b["means3D"], b["rotations"], b["scales"], b["opacities"], features_color=b["shs"],
+                     features_language=b.get("feature"))
+    loss_b = 0
+    for v in range(V):
+        loss_b = loss_b + ((r["render"][v] - tgt_rgb[v]) ** 2).mean()
+        if F:
+            cs = torch.nn.functional.cosine_similarity(r["render_embed"][v].permute(1, 2, 0), tgt_emb[v].permute(1, 2, 0), dim=-1)
+            loss_b = loss_b + lam * (1 - cs.mean())
+    loss_b.backward()
+    assert torch.equal(o["render"], r["render"].detach())
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * abs(float(loss_b))
+    for k in names:
+        assert a[k].grad is not None, k
+        assert util.rel_l2(a[k].grad.cpu().numpy(), b[k].grad.cpu().numpy()) < 2e-5, k
+    assert util.rel_l2(o["viewspace_points"].grad.cpu().numpy(), r["viewspace_points"].grad.cpu().numpy()) < 2e-5
