@@ -33,8 +33,10 @@ static int fail(int code, const std::string& msg)
 	} while (0)
 
 // after each stage: launch errors always, execution errors when debug (the reference's CHECK_CUDA, auxiliary.h:166-173)
+static const bool g_trace = getenv("MGS_TRACE") != nullptr;  // diagnostic: name every stage on stderr as it is enqueued
 #define MGS_STAGE(name)                                                                                  \
 	do {                                                                                                 \
+		if (g_trace) { fprintf(stderr, "[mgs] stage %s enqueued\n", name); fflush(stderr); }            \
 		cudaError_t e_ = cudaGetLastError();                                                             \
 		if (e_ == cudaSuccess && debug) e_ = cudaStreamSynchronize(st);                                  \
 		if (e_ != cudaSuccess)                                                                           \
