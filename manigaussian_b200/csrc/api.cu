@@ -10,6 +10,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 #include "../../include/mgs_rasterizer.h"
 #include "mgs_common.cuh"
@@ -75,16 +76,21 @@ static void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 128)
 	chunk = reinterpret_cast<char*>(ptr + count);
 }
 
-// CUB temp-storage sizes depend only on the item count; the queries are not free (device attribute lookups), so cache them
-// (sizes are taken for the item count rounded up to a power of two: monotone in n, few distinct keys)
+// CUB temp-storage sizes depend on the item count and the device; the queries are not free (device attribute lookups), so
+// cache them.  Sizes are taken for the item count rounded up to the next multiple of 1/8 of its power of two (monotone in
+// n, few distinct keys, at most 12.5 % above the exact need).
 static size_t cached_temp_bytes(int which, int n)
 {
 	static std::mutex mu;
-	static std::map<std::pair<int, int>, size_t> cache;
-	int nb = 1024;
-	while (nb < n && nb < (1 << 30)) nb <<= 1;
+	static std::map<std::tuple<int, int, int>, size_t> cache;
+	int p2 = 1024;
+	while (p2 < n && p2 < (1 << 30)) p2 <<= 1;
+	const int q = std::max(128, p2 >> 3);
+	const int nb = (int)std::min<long long>(((long long)std::max(n, 1) + q - 1) / q * q, (long long)p2);
+	int dev = 0;
+	cudaGetDevice(&dev);
 	std::lock_guard<std::mutex> lk(mu);
-	auto key = std::make_pair(which, nb);
+	auto key = std::make_tuple(dev, which, nb);
 	auto it = cache.find(key);
 	if (it != cache.end()) return it->second;
 	const size_t bytes = which == 0 ? std::max(scan_temp_bytes(nb), depth_sort_temp_bytes(nb)) : tile_sort_temp_bytes(nb);

@@ -46,6 +46,7 @@ class _Alloc:
     def __init__(self, device):
         self.device = device
         self.tensor = None
+        self.error = None  # exception raised inside the C callback (ctypes would swallow it): re-raised by the caller
         self.key = _Alloc._next[0]
         _Alloc._next[0] += 1
         _Alloc._live[self.key] = self
@@ -70,7 +71,28 @@ class _Alloc:
 
 def _alloc_trampoline(user, nbytes):
     a = _Alloc._live.get(int(user or 0))
-    return a.alloc(nbytes) if a is not None else 0
+    if a is None:
+        return 0
+    try:
+        return a.alloc(nbytes)
+    except BaseException as ex:  # e.g. torch.cuda.OutOfMemoryError: hand it to the caller instead of losing it in ctypes
+        a.error = ex
+        return 0
+
+
+def _checked(allocs, rc, what):
+    """_b.check that re-raises an exception stashed by an allocator callback and always releases the allocators"""
+    err = next((a.error for a in allocs if a.error is not None), None)
+    if err is not None:
+        for a in allocs:
+            a.release()
+        raise err
+    try:
+        return _b.check(rc, what)
+    except Exception:
+        for a in allocs:
+            a.release()
+        raise
 
 
 _ALLOC_CB = _b.ALLOC_FN(_alloc_trampoline)
@@ -111,7 +133,7 @@ def rasterize_gaussians_raw(bg, means3D, colors, language_feature, opacity, scal
     rendered = 0
     if P != 0:
         with torch.cuda.device(dev):
-            rendered = _b.check(L.mgs_forward(
+            rendered = _checked((ga, ba, ia), L.mgs_forward(
                 _ALLOC_CB, ga.key, _ALLOC_CB, ba.key, _ALLOC_CB, ia.key,
                 P, int(degree), M, F,
                 _ptr(bg), W, H,
@@ -476,7 +498,7 @@ def _calibrate(L, views, keys, dev, P, degree, M, means3D, sh, colors, opacity, 
         ga, ia = _Alloc(dev), _Alloc(dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         vm, pm, cp = (_prep(x, dev) for x in (s.viewmatrix, s.projmatrix, s.campos))
-        _b.check(L.mgs_forward_begin(_ALLOC_CB, ga.key, _ALLOC_CB, ia.key, P, int(degree), M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors),
+        _checked((ga, ia), L.mgs_forward_begin(_ALLOC_CB, ga.key, _ALLOC_CB, ia.key, P, int(degree), M, W, H, _ptr(means3D), _ptr(sh), _ptr(colors),
                                      _ptr(opacity), _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(vm),
                                      _ptr(pm), _ptr(cp), float(s.tanfovx), float(s.tanfovy), _ptr(radii), counts.data_ptr() + 4 * v,
                                      int(bool(debug)), st.cuda_stream), "mgs_forward_begin")
