@@ -665,7 +665,7 @@ def main_dyna(a, wl, base, cfg, torch, rank, world):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    out["gpu_launches"] = (6 * 2 * V + 4) * a.steps if a.impl == "ours" else 0
+    out["gpu_launches"] = (7 * 2 * V + 4) * a.steps if a.impl == "ours" else 0
     out["roofline"] = {"bound": "hbm", "kernel": "whole pipeline", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                        "traffic": None, "note": "per-kernel roofline is reported by the c3 line (same rasterizer kernels)"}
     if a.impl == "ours" and not a.no_stage_timing:
@@ -952,6 +952,9 @@ def main():
             mv = _binding.profile_read()
             if mv.get("project_bwd", (0, 0))[1] > 0:
                 meas["project_bwd_views_ms"] = round(mv["project_bwd"][0] / mv["project_bwd"][1], 4)
+            # the same stages as they run in the timed region (views on their own streams, kernels of different views
+            # sharing the GPU): the elapsed time of a launch then includes what it waited for its share of the SMs
+            meas["stage_ms_per_launch_overlapped"] = {k: round(v[0] / max(v[1], 1), 4) for k, v in mv.items() if v[1] > 0}
         _binding.profile_enable(False)
     tmax = torch.tensor([ms], device="cuda")
     if dist is not None:
@@ -1039,8 +1042,8 @@ def main():
         per = {k: (v[0] / max(v[1], 1)) for k, v in stages.items()}
         meas["stage_ms_per_launch"] = {k: round(v, 4) for k, v in per.items()}
         # hand-written kernels launched inside the timed region, per view and step: project_fwd, emit_tiles, fill_tail,
-        # ranges_pack, blend_fwd, blend_bwd; plus ONE project_bwd_views per step (multi-view path) or one per view
-        out["gpu_launches"] = (6 * V + 1) * a.steps if streams else 6 * V * a.steps
+        # ranges_pack, tile_order, blend_fwd, blend_bwd; plus ONE project_bwd_views per step (multi-view path) or one per view
+        out["gpu_launches"] = (7 * V + 1) * a.steps if streams else 8 * V * a.steps
         meas["library_launches_cub"] = "depth sort + scan + tile sort (CUB) per view, not counted in gpu_launches"
         dom = max(per, key=per.get)
         if per[dom] <= 0:

@@ -68,6 +68,27 @@ struct StageTimer {
 	}
 };
 
+// MGS_TILE_ORDER=0 launches the blend CTAs in tile order instead of longest-list-first (A/B switch for measurements)
+static bool use_tile_order()
+{
+	static const bool on = [] { const char* e = getenv("MGS_TILE_ORDER"); return !(e && e[0] == '0'); }();
+	return on;
+}
+
+#ifdef MGS_CTA_LOG
+static unsigned long long* g_cta_log = nullptr;
+static unsigned int* g_cta_log_n = nullptr;
+static unsigned int g_cta_log_cap = 0;
+extern "C" int mgs_debug_set_cta_log(void* log, void* counter, unsigned int cap)
+{
+	g_cta_log = static_cast<unsigned long long*>(log); g_cta_log_n = static_cast<unsigned int*>(counter); g_cta_log_cap = cap;
+	return 0;
+}
+#define MGS_CTA_LOG_ARGS(ba) do { (ba).cta_log = g_cta_log; (ba).cta_log_n = g_cta_log_n; (ba).cta_log_cap = g_cta_log_cap; } while (0)
+#else
+#define MGS_CTA_LOG_ARGS(ba) do { } while (0)
+#endif
+
 template <typename T>
 static void obtain(char*& chunk, T*& ptr, size_t count, size_t alignment = 128)
 {
@@ -123,7 +144,7 @@ struct GeomState {
 	}
 };
 struct ImageState {
-	float* final_T; uint32_t* n_contrib; uint2* ranges; int* status;
+	float* final_T; uint32_t* n_contrib; uint2* ranges; int* status; uint32_t* tile_order;
 	static ImageState carve(char*& chunk, size_t N, size_t T)
 	{
 		ImageState s;
@@ -131,6 +152,7 @@ struct ImageState {
 		obtain(chunk, s.n_contrib, N);
 		obtain(chunk, s.ranges, T);
 		obtain(chunk, s.status, 4);  // {instance count, overflow flag} of a forward that did not read the count back
+		obtain(chunk, s.tile_order, T);
 		return s;
 	}
 };
@@ -278,7 +300,7 @@ static int forward_phase2(
 	{
 		StageTimer t_(ST_RANGES_PACK, st);
 		launch_ranges_and_pack(num_rendered, nullptr, num_rendered, (int)T, gx, bin.tile_keys, bin.point_list, geom.means2D, geom.conic_opacity,
-			geom.extent, img.ranges, bin.recs, st);
+			geom.extent, img.ranges, bin.recs, img.tile_order, st);
 	}
 	MGS_STAGE("ranges_pack");
 	}
@@ -286,12 +308,12 @@ static int forward_phase2(
 
 	BlendArgs ba{};
 	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F;
-	ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
+	ba.ranges = img.ranges; ba.tile_order = use_tile_order() ? img.tile_order : nullptr; ba.point_list = bin.point_list; ba.recs = bin.recs;
 	ba.rgbd = geom.rgbd; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
 	ba.want_depth = out_depth != nullptr;
 	ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
 	ba.out_color = out_color; ba.out_feature = out_feature; ba.out_depth = out_depth;
-	{ StageTimer t_(ST_BLEND_FWD, st); launch_blend_fwd(ba, st); }
+	{ StageTimer t_(ST_BLEND_FWD, st); MGS_CTA_LOG_ARGS(ba); launch_blend_fwd(ba, st); }
 	MGS_STAGE("blend_fwd");
 	return num_rendered;
 }
@@ -410,14 +432,14 @@ int mgs_backward(
 
 	BlendArgs ba{};
 	ba.W = width; ba.H = height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F;
-	ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
+	ba.ranges = img.ranges; ba.tile_order = use_tile_order() ? img.tile_order : nullptr; ba.point_list = bin.point_list; ba.recs = bin.recs;
 	ba.rgbd = geom.rgbd; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = background;
 	ba.want_depth = dL_dpix_depth != nullptr;
 	ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
 	ba.dL_dcolor = dL_dpix; ba.dL_dfeature = F > 0 ? dL_dpix_F : nullptr; ba.dL_ddepth = dL_dpix_depth;
 	ba.gb = gb; ba.dL_dfeat = F > 0 ? dL_dfeature : nullptr;
 	if (R > 0) {
-		{ StageTimer t_(ST_BLEND_BWD, st); launch_blend_bwd(ba, st); }
+		{ StageTimer t_(ST_BLEND_BWD, st); MGS_CTA_LOG_ARGS(ba); launch_blend_bwd(ba, st); }
 		MGS_STAGE("blend_bwd");
 	}
 
@@ -478,6 +500,33 @@ static int fork_streams(int V, const mgs_view* views, cudaStream_t join)
 	g_events.put(e);  // recorded and waited on: safe to re-record later (waits captured the earlier record)
 	return 0;
 }
+// every view stream waits for what every OTHER view stream has enqueued so far
+static int cross_wait_streams(int V, const mgs_view* views)
+{
+	std::vector<cudaStream_t> uniq;
+	for (int v = 0; v < V; v++) {
+		cudaStream_t st = reinterpret_cast<cudaStream_t>(views[v].stream);
+		bool seen = false;
+		for (cudaStream_t u : uniq) seen |= u == st;
+		if (!seen) uniq.push_back(st);
+	}
+	if (uniq.size() < 2) return 0;
+	std::vector<cudaEvent_t> ev(uniq.size());
+	for (size_t i = 0; i < uniq.size(); i++) {
+		ev[i] = g_events.get();
+		MGS_CUDA(cudaEventRecord(ev[i], uniq[i]));
+	}
+	for (size_t i = 0; i < uniq.size(); i++)
+		for (size_t j = 0; j < uniq.size(); j++)
+			if (i != j) MGS_CUDA(cudaStreamWaitEvent(uniq[i], ev[j], 0));
+	for (cudaEvent_t e : ev) g_events.put(e);
+	return 0;
+}
+static bool barrier_before_blend()
+{
+	static const bool on = [] { const char* e = getenv("MGS_BLEND_BARRIER"); return e && e[0] == '1'; }();
+	return on;
+}
 // the join stream waits for every view stream
 static int join_streams(int V, const mgs_view* views, cudaStream_t join)
 {
@@ -523,6 +572,16 @@ int mgs_forward_views(
 	// stage by stage across the views: the short per-Gaussian and binning kernels of every view are enqueued before any
 	// view's long blend kernel, so no view's chain queues behind another view's blend
 	for (int phase = 0; phase < 3; phase++) {
+		// MGS_BLEND_BARRIER=1: all blends start together, after the binning chain of EVERY view.  A blend launch is one
+		// wave of single-warp CTAs that takes every shared-memory slot of the GPU, and the short binning kernels of the
+		// other views crawl behind it (CTA timeline, tools/cta_timeline.py: blends 0 and 1 each run alone, 790 us for the
+		// four forward blends of the bench step; started together 590 us) -- but four binning chains side by side take
+		// 0.38 ms instead of 0.22 ms for the first alone, and the step time comes out the same (2.21 ms either way,
+		// DESIGN.md section 7), so the default keeps the dependency-free schedule.
+		if (phase == 2 && barrier_before_blend()) {
+			rc = cross_wait_streams(V, views);
+			if (rc < 0) return rc;
+		}
 		for (int v = 0; v < V; v++) {
 			const mgs_view& w = views[v];
 			cudaStream_t st = reinterpret_cast<cudaStream_t>(w.stream);
@@ -575,14 +634,14 @@ int mgs_forward_views(
 				{
 					StageTimer t_(ST_RANGES_PACK, st);
 					launch_ranges_and_pack(-1, geom.point_offsets + P - 1, (int)cap, (int)T, gx, bin.tile_keys, bin.point_list, geom.means2D,
-						geom.conic_opacity, geom.extent, img.ranges, bin.recs, st);
+						geom.conic_opacity, geom.extent, img.ranges, bin.recs, img.tile_order, st);
 				}
 				MGS_STAGE("ranges_pack");
 				if (w.status) MGS_CUDA(cudaMemcpyAsync(w.status, img.status, 2 * sizeof(int), cudaMemcpyDefault, st));
 			} else {
 				BlendArgs ba{};
 				ba.W = w.width; ba.H = w.height; ba.grid_x = gx; ba.grid_y = gy; ba.F = Fv;
-				ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
+				ba.ranges = img.ranges; ba.tile_order = use_tile_order() ? img.tile_order : nullptr; ba.point_list = bin.point_list; ba.recs = bin.recs;
 				ba.rgbd = geom.rgbd; ba.feature = Fv > 0 ? feature_precomp : nullptr; ba.bg = w.background;
 				ba.want_depth = w.out_depth != nullptr;
 				ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
@@ -594,7 +653,7 @@ int mgs_forward_views(
 					ba.cot_color = w.cot_color; ba.cot_feature = w.cot_feature; ba.loss_acc = w.loss_acc;
 					MGS_CUDA(cudaMemsetAsync(w.loss_acc, 0, 2 * sizeof(float), st));
 				}
-				{ StageTimer t_(ST_BLEND_FWD, st); launch_blend_fwd(ba, st); }
+				{ StageTimer t_(ST_BLEND_FWD, st); MGS_CTA_LOG_ARGS(ba); launch_blend_fwd(ba, st); }
 				MGS_STAGE("blend_fwd");
 			}
 		}
@@ -650,7 +709,7 @@ int mgs_backward_views(
 		MGS_CUDA(cudaMemsetAsync(gb, 0, (size_t)P * GB_STRIDE * sizeof(float), st));
 		BlendArgs ba{};
 		ba.W = w.width; ba.H = w.height; ba.grid_x = gx; ba.grid_y = gy; ba.F = F;
-		ba.ranges = img.ranges; ba.point_list = bin.point_list; ba.recs = bin.recs;
+		ba.ranges = img.ranges; ba.tile_order = use_tile_order() ? img.tile_order : nullptr; ba.point_list = bin.point_list; ba.recs = bin.recs;
 		ba.rgbd = geom.rgbd; ba.feature = F > 0 ? feature_precomp : nullptr; ba.bg = w.background;
 		ba.want_depth = w.dL_dpix_depth != nullptr;
 		ba.final_T = img.final_T; ba.n_contrib = img.n_contrib;
@@ -658,7 +717,7 @@ int mgs_backward_views(
 		ba.gb = gb; ba.dL_dfeat = F > 0 ? dL_dfeature : nullptr;
 		ba.cot_scale = w.cot_scale;
 		if (w.binning_capacity > 0) {
-			{ StageTimer t_(ST_BLEND_BWD, st); launch_blend_bwd(ba, st); }
+			{ StageTimer t_(ST_BLEND_BWD, st); MGS_CTA_LOG_ARGS(ba); launch_blend_bwd(ba, st); }
 			MGS_STAGE("blend_bwd");
 		}
 	}

@@ -197,13 +197,45 @@ __global__ void __launch_bounds__(256) ranges_pack_kernel(int R_host, const uint
 	dst[1] = make_float4(co.z, co.w, __uint_as_float(mask), __uint_as_float(g));
 }
 
+// Launch order of the blend CTAs: tiles by descending list length (rank by counting, ties by tile id).  The blend grids
+// are about one wave of single-warp CTAs whose run time follows the list length; starting the long ones first leaves
+// the short ones for the tail of the wave (and of the last view's kernel in a multi-view step).
+__global__ void __launch_bounds__(256) tile_order_kernel(const uint2* __restrict__ ranges, int T, uint32_t* __restrict__ order)
+{
+	__shared__ uint32_t s_len[256];
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t mine = 0;
+	if (t < T) { const uint2 r = ranges[t]; mine = r.y - r.x; }
+	uint32_t rank = 0;
+	for (int base = 0; base < T; base += 256) {
+		const int u = base + threadIdx.x;
+		uint32_t len = 0;
+		if (u < T) { const uint2 r = ranges[u]; len = r.y - r.x; }
+		__syncthreads();
+		s_len[threadIdx.x] = len;
+		__syncthreads();
+		const int m = min(256, T - base);
+		for (int i = 0; i < m; i++) {
+			const uint32_t l = s_len[i];
+			rank += (l > mine || (l == mine && base + i < t)) ? 1u : 0u;
+		}
+	}
+	if (t < T) order[rank] = (uint32_t)t;
+}
+
+void launch_tile_order(const uint2* ranges, int num_tiles, uint32_t* order, cudaStream_t s)
+{
+	if (num_tiles > 0) tile_order_kernel<<<ceil_div(num_tiles, 256), 256, 0, s>>>(ranges, num_tiles, order);
+}
+
 void launch_ranges_and_pack(int R, const uint32_t* R_dev, int capacity, int num_tiles, int grid_x, const uint32_t* tile_keys,
 	const uint32_t* point_list, const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs,
-	cudaStream_t s)
+	uint32_t* tile_order, cudaStream_t s)
 {
 	cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s);
 	const int n = R >= 0 ? R : capacity;
 	if (n > 0) ranges_pack_kernel<<<ceil_div(n, 256), 256, 0, s>>>(R, R_dev, capacity, grid_x, tile_keys, point_list, means2D, conic_opacity, extent, ranges, recs);
+	if (tile_order) launch_tile_order(ranges, num_tiles, tile_order, s);
 }
 
 }  // namespace mgs

@@ -77,9 +77,13 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 	__shared__ __align__(16) float s_g[16 * GS];           // cotangent rows of the block's pixels
 	__shared__ __align__(8) uint64_t s_bar[RING];
 
+#ifdef MGS_CTA_LOG
+	const unsigned long long t_start = cta_log_now();
+#endif
 	const int lane = threadIdx.x;
 	const int gid = lane >> 2, tig = lane & 3;
-	const int tile = blockIdx.x >> 3, sub = blockIdx.x & 7;
+	const int sub = blockIdx.x & 7;
+	const int tile = a.tile_order ? (int)a.tile_order[blockIdx.x >> 3] : (int)(blockIdx.x >> 3);  // longest lists first
 	const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
 	const int bx0 = tile_x * TILE_X + (sub & 1) * WARP_BX;
 	const int by0 = tile_y * TILE_Y + (sub >> 1) * WARP_BY;
@@ -429,6 +433,9 @@ __global__ void __launch_bounds__(32, MGS_BWD_MIN_CTAS) blend_bwd_kernel(BlendAr
 		if (qcount == 0) break;
 		process_chunk(min(qcount, BWD_CH));
 	}
+#ifdef MGS_CTA_LOG
+	cta_log_put(a, t_start, 1u, (unsigned int)sub, maxc);
+#endif
 }
 
 bool feature_rows_vectorizable(const float* feature, int F);

@@ -68,4 +68,26 @@ struct WarpRecRingT {
 	__device__ __forceinline__ const float4* buffer(int k) const { return reinterpret_cast<const float4*>(buf + (k % RING) * BATCH); }
 };
 
+#ifdef MGS_CTA_LOG
+__device__ __forceinline__ unsigned long long cta_log_now()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+__device__ __forceinline__ void cta_log_put(const BlendArgs& a, unsigned long long t0, unsigned int kind, unsigned int sub, unsigned int len)
+{
+	if (a.cta_log == nullptr || threadIdx.x != 0) return;
+	const unsigned long long t1 = cta_log_now();
+	const unsigned int i = atomicAdd(a.cta_log_n, 1u);
+	if (i >= a.cta_log_cap) return;
+	unsigned int sm;
+	asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+	unsigned long long* o = a.cta_log + 4 * (size_t)i;
+	o[0] = t0; o[1] = t1;
+	o[2] = (unsigned long long)(kind | (sub << 8)) | ((unsigned long long)len << 32);
+	o[3] = (unsigned long long)sm | ((unsigned long long)blockIdx.x << 32);
+}
+#endif
+
 }  // namespace mgs

@@ -55,9 +55,13 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 	__shared__ __align__(16) float s_w[FWD_CH * 32];      // blend weights, per k-step [tig][gid][mt][e][h]: survivor 8 ks + tig + 4 e, pixel 4 gid + 2 mt + h
 	__shared__ __align__(8) uint64_t s_bar[RING];
 
+#ifdef MGS_CTA_LOG
+	const unsigned long long t_start = cta_log_now();
+#endif
 	const int lane = threadIdx.x;
 	const int gid = lane >> 2, tig = lane & 3;
-	const int tile = blockIdx.x >> 3, sub = blockIdx.x & 7;
+	const int sub = blockIdx.x & 7;
+	const int tile = a.tile_order ? (int)a.tile_order[blockIdx.x >> 3] : (int)(blockIdx.x >> 3);  // longest lists first
 	const int tile_x = tile % a.grid_x, tile_y = tile / a.grid_x;
 	const int bx0 = tile_x * TILE_X + (sub & 1) * WARP_BX;
 	const int by0 = tile_y * TILE_Y + (sub >> 1) * WARP_BY;
@@ -78,9 +82,12 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 	int issued = 0, waited = 0;
 	for (; issued < min(nb, RING); issued++) ring.issue(issued);
 
-	float T = 1.0f;
+	// T is the running product of (1 - alpha) over every evaluated pair, the stopping pair included: the product only
+	// shrinks, so once one test T (1 - alpha) < 1e-4 has failed every later one fails too and no "done" flag has to sit
+	// in the recurrence (the reference stops looking at that point; here the later pairs get zero weight).  T_out is the
+	// transmittance after the last accepted pair = the reference's final T.  Pixels outside the image start at 0.
+	float T = inside ? 1.0f : 0.0f, T_out = 1.0f;
 	uint32_t last_contributor = 0;
-	bool done = !inside;
 	float acc[2][NT][4];
 #pragma unroll
 	for (int mt = 0; mt < 2; mt++)
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 		const int nks = (cnt + 7) >> 3;
 		int ks = 0;
 		for (; ks < nks; ks++) {
-			if (ks > 0 && __all_sync(0xffffffffu, done)) break;
+			if (ks > 0 && __all_sync(0xffffffffu, T < T_STOP)) break;
 			const float4* q4 = s_q + 16 * ks;
 			float* wrow = s_w + 256 * ks;
 			float al[8];      // alpha of the pair, 0 where the pair is skipped (power > 0, alpha < 1/255, empty slot)
@@ -145,14 +152,12 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 #pragma unroll
 			for (int u = 0; u < 8; u++) {
 				const float alpha = al[u];
-				const bool cand = !done && (alpha != 0.f);
 				const float test_T = T * (1 - alpha);
-				const bool stop = cand && (test_T < T_STOP);
-				const bool use = cand && !stop;
+				const bool use = !(test_T < T_STOP);  // a skipped pair (alpha = 0) passes with zero weight and T unchanged
 				wrow[(u & 3) * 64 + (u >> 2) * 2 + wofs] = use ? alpha * T : 0.f;
-				done = done || stop;
-				T = use ? test_T : T;
-				last_contributor = use ? ps[u] : last_contributor;
+				T_out = use ? test_T : T_out;
+				last_contributor = (use && alpha != 0.f) ? ps[u] : last_contributor;
+				T = test_T;
 			}
 		}
 		const int nk = ks;  // k-steps to contract
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 		if (lane < left) { s_q[2 * lane] = m0; s_q[2 * lane + 1] = m1; }
 		qcount = left;
 		__syncwarp();
-		return __all_sync(0xffffffffu, done);
+		return __all_sync(0xffffffffu, T < T_STOP);
 	};
 
 	// Fill the queue from the record stream, run a chunk whenever FWD_CH survivors are queued, and the remainder at the
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 	const size_t HW = (size_t)a.H * a.W;
 	if (inside) {
 		const size_t pix = (size_t)a.W * pyi + pxi;
+		T = T_out;
 		a.final_T[pix] = T;
 		a.n_contrib[pix] = last_contributor;
 	}
@@ -340,6 +346,9 @@ __global__ void __launch_bounds__(32, MGS_FWD_MIN_CTAS) blend_fwd_kernel(BlendAr
 			if (embed) red_add(a.loss_acc + 1, s_cos);
 		}
 	}
+#ifdef MGS_CTA_LOG
+	cta_log_put(a, t_start, 0u, (unsigned int)sub, range.y - range.x);
+#endif
 }
 
 int blend_supported(int F) { return F >= 0 && F <= 32; }

@@ -75,6 +75,7 @@ struct BlendArgs {
 	int grid_x, grid_y;
 	int F;                       // user feature channels (0 = none)
 	const uint2* ranges;         // [T]
+	const uint32_t* tile_order;  // [T] launch order of the tiles (CTA group i works on tile tile_order[i]); null = identity
 	const uint32_t* point_list;  // [R] sorted Gaussian ids
 	const InstRec* recs;         // [R] sorted packed records
 	const float4* rgbd;          // [P] {r,g,b,depth}
@@ -103,6 +104,11 @@ struct BlendArgs {
 	float* cot_feature;
 	float* loss_acc;
 	const float* cot_scale;
+#ifdef MGS_CTA_LOG
+	// measurement build only (tools/cta_timeline.py): every blend CTA appends {t0, t1 (globaltimer ns), kind | sub << 8, list length,
+	// SM id, block id} -- the timeline of the single-warp CTAs across kernels and streams
+	unsigned long long* cta_log; unsigned int* cta_log_n; unsigned int cta_log_cap;
+#endif
 };
 // loss_heads.cu: the same heads for images that already sit in memory (planar [3,H,W] / [F,H,W], V views in one launch)
 void launch_loss_heads(int V, int F, int N, const float* color, const float* feature, const float* tgt_color, const float* tgt_feature,
@@ -157,8 +163,9 @@ void launch_fill_tail(const uint32_t* offsets, int P, uint32_t capacity, uint32_
 void launch_tile_sort(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
 	const uint32_t* vals_in, uint32_t* vals_out, int R, int end_bit, cudaStream_t s);
 // R < 0: the instance count is read on the device from *R_dev (clamped to `capacity`), the grid covers `capacity`
+void launch_tile_order(const uint2* ranges, int num_tiles, uint32_t* order, cudaStream_t s);
 void launch_ranges_and_pack(int R, const uint32_t* R_dev, int capacity, int num_tiles, int grid_x, const uint32_t* tile_keys, const uint32_t* point_list,
-	const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs, cudaStream_t s);
+	const float2* means2D, const float4* conic_opacity, const float2* extent, uint2* ranges, InstRec* recs, uint32_t* tile_order, cudaStream_t s);
 
 // blend_fwd.cu / blend_bwd.cu
 int blend_supported(int F);

@@ -37,30 +37,42 @@ __device__ __forceinline__ float dot3(const float* u, const float* v) { return u
 
 }  // namespace
 
-__global__ void __launch_bounds__(128) project_bwd_views_kernel(ProjectBwdViewsArgs a)
+// NSH = floats of SH gradient kept in registers (3 (deg + 1)^2 for the largest degree the instantiation serves): the
+// kernel is latency bound (dependent loads per view, ~1000 instructions per Gaussian), so registers = occupancy = speed;
+// degree <= 1 (ManiGaussian's setting) runs at 5 blocks per SM instead of 3.
+#ifndef MGS_PBWD_MINB
+#define MGS_PBWD_MINB 5
+#endif
+template <int NSH, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) project_bwd_views_kernel(ProjectBwdViewsArgs a)
 {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= a.P) return;
 	const float p[3] = { a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2] };
 
 	// ---- the Gaussian's own covariance: S = L L^T, L = R(q) diag(mod * s), or the caller's ----
-	float R[3][3], se[3] = { 0.f, 0.f, 0.f }, q4[4] = { 0.f, 0.f, 0.f, 0.f };
+	// (only S, q and s live across the view loop; R(q) is rebuilt for the chain to scale / rotation at the end)
+	float se[3] = { 0.f, 0.f, 0.f }, q4[4] = { 0.f, 0.f, 0.f, 0.f };
 	float S[3][3];
 	const bool from_sr = a.scales != nullptr;
-	if (from_sr) {
-#pragma unroll
-		for (int i = 0; i < 4; i++) q4[i] = a.rotations[4 * (size_t)idx + i];
+	auto rotation = [&](float R[3][3]) {
 		const float r = q4[0], x = q4[1], y = q4[2], z = q4[3];
 		R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
 		R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
 		R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
+	};
+	if (from_sr) {
+		const float4 qv = *reinterpret_cast<const float4*>(a.rotations + 4 * (size_t)idx);
+		q4[0] = qv.x; q4[1] = qv.y; q4[2] = qv.z; q4[3] = qv.w;
+		float R[3][3];
+		rotation(R);
 #pragma unroll
 		for (int j = 0; j < 3; j++) se[j] = a.scale_modifier * a.scales[3 * (size_t)idx + j];
 #pragma unroll
 		for (int i = 0; i < 3; i++)
 #pragma unroll
-			for (int j = 0; j < 3; j++)
-				S[i][j] = R[i][0] * se[0] * se[0] * R[j][0] + R[i][1] * se[1] * se[1] * R[j][1] + R[i][2] * se[2] * se[2] * R[j][2];
+			for (int j = i; j < 3; j++)
+				S[i][j] = S[j][i] = R[i][0] * se[0] * se[0] * R[j][0] + R[i][1] * se[1] * se[1] * R[j][1] + R[i][2] * se[2] * se[2] * R[j][2];
 	} else {
 		const float* c = a.cov3D_precomp + 6 * (size_t)idx;
 		S[0][0] = c[0]; S[0][1] = S[1][0] = c[1]; S[0][2] = S[2][0] = c[2];
@@ -71,19 +83,22 @@ __global__ void __launch_bounds__(128) project_bwd_views_kernel(ProjectBwdViewsA
 	float gp[3] = { 0.f, 0.f, 0.f };                       // dL/dp
 	float D[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };         // dL/dS, entries 00 01 02 11 12 22 of the symmetric matrix
 	float gop = 0.f, gcol[3] = { 0.f, 0.f, 0.f }, gm2[2] = { 0.f, 0.f };
-	float gsh[48];
+	float gsh[NSH];
 #pragma unroll
-	for (int i = 0; i < 48; i++) gsh[i] = 0.f;
+	for (int i = 0; i < NSH; i++) gsh[i] = 0.f;
 	const float* sh = a.shs ? a.shs + (size_t)idx * a.M * 3 : nullptr;
-	const int deg = a.D;
+	const int deg = min(a.D, NSH >= 48 ? 3 : NSH >= 27 ? 2 : 1);
 
 	for (int v = 0; v < a.V; v++) {
 		const ProjectBwdView& w = a.view[v];
+		// the view's record is loaded before the radius is known (the scratch row of an invisible Gaussian is zero-filled
+		// memory, never unmapped): the four loads of a view overlap instead of queueing behind the radius
+		const float4* gb = reinterpret_cast<const float4*>(w.gb + (size_t)idx * GB_STRIDE);
+		const float4 g0 = gb[0], g1 = gb[1], g2 = gb[2];
+		const uint8_t cl = sh ? w.clamped[idx] : (uint8_t)0;
 		const bool live = w.radii[idx] > 0;
 		float dm[2] = { 0.f, 0.f };
 		if (live) {
-			const float4* gb = reinterpret_cast<const float4*>(w.gb + (size_t)idx * GB_STRIDE);
-			const float4 g0 = gb[0], g1 = gb[1], g2 = gb[2];
 			dm[0] = g0.x; dm[1] = g0.y;
 			const float gA = g0.z, gB = g0.w, gC = g1.x;        // dL/dconic (xx, xy halved, yy)
 			const float dcol[3] = { g1.z, g1.w, g2.x };
@@ -152,7 +167,6 @@ __global__ void __launch_bounds__(128) project_bwd_views_kernel(ProjectBwdViewsA
 			}
 			// colour -> SH coefficients, and through the view direction into the mean
 			if (sh) {
-				const uint8_t cl = w.clamped[idx];
 				const float dRGB[3] = { (cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2] };
 				const float vx = p[0] - w.cam_pos[0], vy = p[1] - w.cam_pos[1], vz = p[2] - w.cam_pos[2];
 				const float il = 1.0f / sqrtf(vx * vx + vy * vy + vz * vz);
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(128) project_bwd_views_kernel(ProjectBwdViewsA
 				// coefficient k: basis value B and its gradient (bx, by, bz) w.r.t. the direction
 				auto term = [&](int k, float B, float bx, float by, float bz) {
 					const float s = sh[3 * k] * dRGB[0] + sh[3 * k + 1] * dRGB[1] + sh[3 * k + 2] * dRGB[2];
-					gsh[3 * k] += B * dRGB[0]; gsh[3 * k + 1] += B * dRGB[1]; gsh[3 * k + 2] += B * dRGB[2];
+					if (3 * k + 2 < NSH) { gsh[3 * k] += B * dRGB[0]; gsh[3 * k + 1] += B * dRGB[1]; gsh[3 * k + 2] += B * dRGB[2]; }
 					dd[0] += bx * s; dd[1] += by * s; dd[2] += bz * s;
 				};
 				term(0, kSh.c0, 0.f, 0.f, 0.f);
@@ -170,14 +184,14 @@ __global__ void __launch_bounds__(128) project_bwd_views_kernel(ProjectBwdViewsA
 					term(2, kSh.c1 * z, 0.f, 0.f, kSh.c1);
 					term(3, -kSh.c1 * x, -kSh.c1, 0.f, 0.f);
 				}
-				if (deg > 1) {
+				if (NSH >= 27 && deg > 1) {
 					const float xx = x * x, yy = y * y, zz = z * z;
 					term(4, kSh.c2[0] * x * y, kSh.c2[0] * y, kSh.c2[0] * x, 0.f);
 					term(5, kSh.c2[1] * y * z, 0.f, kSh.c2[1] * z, kSh.c2[1] * y);
 					term(6, kSh.c2[2] * (2.f * zz - xx - yy), -2.f * kSh.c2[2] * x, -2.f * kSh.c2[2] * y, 4.f * kSh.c2[2] * z);
 					term(7, kSh.c2[3] * x * z, kSh.c2[3] * z, 0.f, kSh.c2[3] * x);
 					term(8, kSh.c2[4] * (xx - yy), 2.f * kSh.c2[4] * x, -2.f * kSh.c2[4] * y, 0.f);
-					if (deg > 2) {
+					if (NSH >= 48 && deg > 2) {
 						term(9, kSh.c3[0] * y * (3.f * xx - yy), kSh.c3[0] * 6.f * x * y, kSh.c3[0] * 3.f * (xx - yy), 0.f);
 						term(10, kSh.c3[1] * x * y * z, kSh.c3[1] * y * z, kSh.c3[1] * x * z, kSh.c3[1] * x * y);
 						term(11, kSh.c3[2] * y * (4.f * zz - xx - yy), kSh.c3[2] * -2.f * x * y, kSh.c3[2] * (4.f * zz - xx - 3.f * yy), kSh.c3[2] * 8.f * y * z);
@@ -204,6 +218,8 @@ __global__ void __launch_bounds__(128) project_bwd_views_kernel(ProjectBwdViewsA
 	float dscale[3] = { 0.f, 0.f, 0.f }, drot[4] = { 0.f, 0.f, 0.f, 0.f };
 	if (from_sr) {
 		const float Dm[3][3] = { { D[0], D[1], D[2] }, { D[1], D[3], D[4] }, { D[2], D[4], D[5] } };
+		float R[3][3];
+		rotation(R);
 		float A[3][3];  // dL/dR = (2 D L) diag(s),  L = R diag(s)
 #pragma unroll
 		for (int j = 0; j < 3; j++) {
@@ -251,14 +267,20 @@ __global__ void __launch_bounds__(128) project_bwd_views_kernel(ProjectBwdViewsA
 		float* o = a.dL_dsh + (size_t)idx * a.M * 3;
 		const int used = sh ? 3 * (deg + 1) * (deg + 1) : 0;
 #pragma unroll
-		for (int i = 0; i < 48; i++)
+		for (int i = 0; i < NSH; i++)
 			if (i < 3 * a.M) put(o + i, i < used ? gsh[i] : 0.f);
+		for (int i = NSH; i < 3 * a.M; i++) put(o + i, 0.f);  // coefficients above the active degree
 	}
 }
 
 void launch_project_bwd_views(const ProjectBwdViewsArgs& a, cudaStream_t s)
 {
-	if (a.P > 0 && a.V > 0) project_bwd_views_kernel<<<ceil_div(a.P, 128), 128, 0, s>>>(a);
+	if (a.P <= 0 || a.V <= 0) return;
+	const int grid = ceil_div(a.P, 128);
+	const int deg = a.shs ? a.D : 0;
+	if (deg <= 1) project_bwd_views_kernel<12, MGS_PBWD_MINB><<<grid, 128, 0, s>>>(a);
+	else if (deg == 2) project_bwd_views_kernel<27, 4><<<grid, 128, 0, s>>>(a);
+	else project_bwd_views_kernel<48, 3><<<grid, 128, 0, s>>>(a);
 }
 
 }  // namespace mgs

@@ -13,6 +13,8 @@ compiled in (config.h:16), and `return_depth=True` adds a view-space depth plane
 """
 from typing import NamedTuple
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -416,6 +418,8 @@ def _status_slots(n):
 
 
 def _view_streams(device, n):
+    if os.environ.get("MGS_ONE_STREAM"):  # measurement hook: every view on the caller's stream (no overlap between views)
+        return [torch.cuda.current_stream(device)] * n
     key = (device.index if device.index is not None else torch.cuda.current_device())
     pool = _VIEW_STREAMS.setdefault(key, [])
     while len(pool) < n:
