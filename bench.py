@@ -327,7 +327,11 @@ def make_render(impl_name, wl, torch):
     return render, GaussianRasterizationSettings
 
 
-def make_e2e(impl_name, wl, torch, dist=None):
+def make_e2e(impl_name, wl, torch, dist=None, heads=False):
+    """heads=True: the step's loss is ManiGaussian's two rendering heads on every view (L2 on the colour image + cosine
+    embedding loss on the feature image, agents/manigaussian_bc/loss.py:12-23 as neural_rendering.py:300-318 applies them),
+    the uploaded image tensors serving as the ground truth; ours computes them in the blend epilogue (render_views(targets=)),
+    the reference arm with the PyTorch ops of its own loss.py."""
     P, F = wl["P"], wl["F"]
     render, GaussianRasterizationSettings = make_render(impl_name, wl, torch)
     copy_stream = torch.cuda.Stream()
@@ -415,6 +419,16 @@ def make_e2e(impl_name, wl, torch, dist=None):
             from manigaussian_b200.gaussian_renderer import render_views
             views = [GaussianRasterizationSettings(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], cam["bg"], 1.0, cam["viewmatrix"],
                                                    cam["projmatrix"], SH_DEGREE, cam["campos"], False, False, F > 0) for cam in C]
+            if heads:
+                tg = {"rgb": torch.stack([ct["dL_dcolor"] for ct in T])}
+                if F:
+                    tg["embed"] = torch.stack([ct["dL_dfeature"] for ct in T])
+                o = render_views(views, G["means3D"], G["rotations"], G["scales"], G["opacities"], features_color=G["shs"],
+                                 features_language=G["feature"] if F else None, normalize_feature=False, targets=tg,
+                                 sync_gradients=True if dist is not None else None)
+                loss = o["loss_rgb"].sum() + (o["loss_embed"].sum() if F else 0.0)
+                loss.backward()
+                return read_back(loss)
             o = render_views(views, G["means3D"], G["rotations"], G["scales"], G["opacities"], features_color=G["shs"],
                              features_language=G["feature"] if F else None, return_depth=wl["depth"], normalize_feature=False,
                              sync_gradients=True if dist is not None else None)  # N > 1: the one all-reduce, inside the backward
@@ -432,6 +446,14 @@ def make_e2e(impl_name, wl, torch, dist=None):
             out = render(st, means3D=G["means3D"], means2D=torch.zeros_like(G["means3D"], requires_grad=True),
                          opacities=G["opacities"], shs=G["shs"], language_feature_precomp=G["feature"] if F else None,
                          scales=G["scales"], rotations=G["rotations"])
+            if heads:
+                # the reference's own heads (loss.py:12-13, 18-23); its cosine head works on [..., F] rows
+                lv = ((out[0] - ct["dL_dcolor"]) ** 2).mean()
+                if F:
+                    pe, ge = out[1].permute(1, 2, 0), ct["dL_dfeature"].permute(1, 2, 0)
+                    lv = lv + (1.0 - torch.nn.functional.cosine_similarity(pe, ge, dim=-1).mean())
+                losses.append(lv)
+                continue
             lv = (out[0] * ct["dL_dcolor"]).sum()
             if F:
                 lv = lv + (out[1] * ct["dL_dfeature"]).sum()
@@ -483,6 +505,13 @@ def make_e2e(impl_name, wl, torch, dist=None):
         cd = torch.stack([ct["dL_ddepth"] for ct in T]) if wl["depth"] else None
 
         def fwd_bwd():
+            if heads:
+                o = render_views(views, G["means3D"], G["rotations"], G["scales"], G["opacities"], features_color=G["shs"],
+                                 features_language=G["feature"] if F else None, normalize_feature=False,
+                                 targets={"rgb": cc, "embed": cf} if F else {"rgb": cc})
+                loss = o["loss_rgb"].sum() + (o["loss_embed"].sum() if F else 0.0)
+                loss.backward()
+                return loss
             o = render_views(views, G["means3D"], G["rotations"], G["scales"], G["opacities"], features_color=G["shs"],
                              features_language=G["feature"] if F else None, return_depth=wl["depth"], normalize_feature=False)
             loss = (o["render"] * cc).sum()
@@ -818,6 +847,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-graph", action="store_true", help="also time the e2e step replayed from a CUDA graph (always done for small clouds)")
+    ap.add_argument("--heads", action="store_true", help="e2e: the loss is ManiGaussian's L2-colour + cosine-embedding heads per view "
+                    "(ours: fused into the blend kernels; reference: its PyTorch ops) instead of a fixed cotangent")
     ap.add_argument("--no-c5", action="store_true", help="skip the strong-scaling block (BASELINE configs[4]: 1M Gaussians, 8 views over the ranks)")
     ap.add_argument("--settle", type=float, default=1.5, help="seconds of untimed steps before the W warm-up steps "
                     "(lets clocks/power state and the caching allocator reach steady state)")
@@ -967,7 +998,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         Gh, Ch, Th = to_device(g, cams, cts, torch, pinned=True)
-        step = make_e2e(a.impl, wl, torch, dist)
+        step = make_e2e(a.impl, wl, torch, dist, heads=a.heads)
         e2e_state = {}
         for _ in range(max(3, a.warmup)):
             step(Gh, Ch, Th, e2e_state)
@@ -987,7 +1018,9 @@ def main():
                "note": "wall clock around K steps; every step copies all its inputs pinned-host->device (prefetched one step ahead on a "
                        "copy stream), runs the public autograd API (ours: manigaussian_b200.gaussian_renderer.render_views, one node "
                        "for all views; reference: its autograd Function per view), and copies the loss to pinned host memory (async, value consumed one "
-                       "step later, all K read before the clock stops)"}
+                       "step later, all K read before the clock stops)",
+               "loss": "L2 colour + cosine embedding heads per view (ours: fused in the blend kernels; reference: PyTorch ops)" if a.heads
+                       else "sum(image * fixed cotangent)"}
 
     if e2e is not None and a.impl == "ours" and world == 1 and (a.e2e_graph or P <= 100_000):
         try:

@@ -208,17 +208,18 @@ class _RasterizeViewsLoss(torch.autograd.Function):
         loss_embed = 1.0 - loss_acc[:, 1] / N if target_embed is not None else torch.zeros((V,), **opts)
         radii = torch.stack([o[3] for o in outs])
         ctx.views, ctx.streams, ctx.group = views, streams, group
-        ctx.outs = outs
+        # capacity, radii and the three state buffers per view -- never the images: they are views of this node's outputs, and an
+        # output kept on ctx is a reference cycle (output -> grad_fn -> ctx -> output) that leaks the whole step
+        ctx.state = [(o[0], o[3], o[4], o[5], o[6]) for o in outs]
         ctx.include, ctx.F, ctx.degree = include, F, degree
         ctx.opac_shape = opacities.shape
         ctx.cots = (cot_rgb, cot_embed)
         ctx.save_for_backward(means3D, sh if sh is not None else torch.empty(0, device=dev),
                               colors_precomp if colors_precomp is not None else torch.empty(0, device=dev),
                               feature if include else torch.empty(0, device=dev), scales, rotations)
-        ctx.mark_non_differentiable(radii, color)
+        # ONE call: a second mark_non_differentiable replaces the first
+        ctx.mark_non_differentiable(*([radii, color] + ([feat_img] if include else [])))
         empty = torch.empty(0, device=dev)
-        if include:
-            ctx.mark_non_differentiable(feat_img)
         return loss_rgb, loss_embed, color, (feat_img if include else empty), radii
 
     @staticmethod
@@ -234,7 +235,8 @@ class _RasterizeViewsLoss(torch.autograd.Function):
         pk = PackedGradients(P, ctx.F, M, dev, colors=use_colors, zero=False)
         grp = None if ctx.group in (None, True) else ctx.group
         m2d = torch.empty((V, P, 3), dtype=torch.float32, device=dev)
-        rasterize_views_backward_raw(views, ctx.outs, ctx.streams, cot_rgb, cot_embed if ctx.include else None, means3D,
+        outs = [(R, None, None, radii, geom, binb, img) for (R, radii, geom, binb, img) in ctx.state]
+        rasterize_views_backward_raw(views, outs, ctx.streams, cot_rgb, cot_embed if ctx.include else None, means3D,
                                      colors_precomp if use_colors else None, feature if ctx.include else None, scales, rotations,
                                      views[0].scale_modifier, None, sh if M else None, ctx.degree, ctx.include, debug=views[0].debug,
                                      accumulate_into=pk.views, means2D_per_view=m2d, cot_scale=scale,

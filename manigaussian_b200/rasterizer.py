@@ -284,7 +284,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                                                 s.scale_modifier, cov3Ds_precomp, sh, s.sh_degree, s.include_feature,
                                                 return_depth=return_depth)
             out = outs[0]
-            ctx.async_view = (outs, streams)
+            # only the capacity and the streams: the images and radii in `outs` are OUTPUTS of this node, and an output kept on
+            # ctx is a reference cycle (output -> grad_fn -> ctx -> output) that no collector frees -- the state buffers and the
+            # radii come back through saved_tensors in the backward
+            ctx.async_view = (int(out[0]), streams)
         else:
             out = rasterize_gaussians_raw(*args, return_depth=return_depth)
         num_rendered, color, language_feature, radii, geomBuffer, binningBuffer, imgBuffer = out[:7]
@@ -315,7 +318,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 imgBuffer, s.debug, s.include_feature)
         depth_grad = grad_out_depth if ctx.return_depth else None
         if ctx.async_view is not None:
-            outs, streams = ctx.async_view
+            cap, streams = ctx.async_view
+            outs = [ViewOut((cap, None, None, radii, geomBuffer, binningBuffer, imgBuffer))]
             grads = rasterize_views_backward_raw(
                 [s], outs, streams, [grad_out_color], [grad_out_language_feature] if s.include_feature else None, means3D,
                 colors_precomp, language_feature_precomp, scales, rotations, s.scale_modifier, cov3Ds_precomp, sh, s.sh_degree,

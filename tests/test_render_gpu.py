@@ -376,3 +376,54 @@ def test_loss_heads_fused_into_the_blend_epilogue(F, lam):
         assert a[k].grad is not None, k
         assert util.rel_l2(a[k].grad.cpu().numpy(), b[k].grad.cpu().numpy()) < 2e-5, k
     assert util.rel_l2(o["viewspace_points"].grad.cpu().numpy(), r["viewspace_points"].grad.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("path", ["module", "render_views", "render_views_depth", "loss_heads"])
+def test_steps_do_not_accumulate_device_memory(path):
+    """A training loop must come back to the same allocated bytes after every step.  An autograd Function that keeps one of
+    its OUTPUTS on ctx builds the cycle output -> grad_fn -> ctx -> output, which neither reference counting nor the
+    garbage collector frees: every step's images, state buffers and -- through the graph -- its input leaves stay alive."""
+    import gc
+    import torch
+    from manigaussian_b200 import GaussianRasterizer
+    from manigaussian_b200.gaussian_renderer import render_views
+    P, F, W, H, V = 6000, 32, 64, 48, 2
+    g = _cloud(P, F, 33)
+    cams = _cams(V, W, H)
+    host = {k: np.asarray(g[k], np.float32) for k in ("means3D", "rotations", "scales", "opacities", "shs", "feature")}
+    tgt = (torch.rand(V, 3, H, W, device="cuda"), torch.randn(V, F, H, W, device="cuda"))
+
+    def step():
+        L = {k: _t(v).requires_grad_(True) for k, v in host.items()}  # fresh leaves every step, like a network's outputs
+        if path == "module":
+            s = cams.settings(0, torch.zeros(3, device="cuda"), 1, True)
+            img, emb, _ = GaussianRasterizer(s)(means3D=L["means3D"], means2D=torch.zeros_like(L["means3D"]), opacities=L["opacities"],
+                                                shs=L["shs"], language_feature_precomp=L["feature"], scales=L["scales"],
+                                                rotations=L["rotations"])
+            loss = (img * tgt[0][0]).sum() + (emb * tgt[1][0]).sum()
+        elif path == "loss_heads":
+            o = render_views(cams, L["means3D"], L["rotations"], L["scales"], L["opacities"], features_color=L["shs"],
+                             features_language=L["feature"], targets={"rgb": tgt[0], "embed": tgt[1]})
+            loss = o["loss_rgb"].sum() + 0.01 * o["loss_embed"].sum()
+        else:
+            o = render_views(cams, L["means3D"], L["rotations"], L["scales"], L["opacities"], features_color=L["shs"],
+                             features_language=L["feature"], return_depth=(path == "render_views_depth"))
+            loss = (o["render"] * tgt[0]).sum() + (o["render_embed"] * tgt[1]).sum()
+            if path == "render_views_depth":
+                loss = loss + o["depth"].sum()
+        loss.backward()
+        return float(loss)
+
+    gc.disable()
+    try:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        base = torch.cuda.memory_allocated()
+        for _ in range(4):
+            step()
+        torch.cuda.synchronize()
+        grown = torch.cuda.memory_allocated() - base
+    finally:
+        gc.enable()
+    assert grown == 0, f"{grown} bytes stayed allocated after 4 more steps"
