@@ -1004,12 +1004,18 @@ def main():
             step(Gh, Ch, Th, e2e_state)
         step.flush()
         barrier()
+        per_step = []
         t0 = time.perf_counter()
         for _ in range(a.steps):
+            ts = time.perf_counter()
             step(Gh, Ch, Th, e2e_state)
+            per_step.append(time.perf_counter() - ts)
         step.flush()
         barrier()
         te = torch.tensor([(time.perf_counter() - t0) / a.steps], device="cuda")
+        per_step.sort()
+        meas["e2e_host_ms_per_call"] = {"min": round(per_step[0] * 1e3, 3), "median": round(per_step[len(per_step) // 2] * 1e3, 3),
+                                        "max": round(per_step[-1] * 1e3, 3)}
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": P * V * world / float(te.item()), "unit": "Gaussians/s",

@@ -22,5 +22,7 @@ for w in c3 mg; do for impl in ours reference; do
   timeout 600 python bench.py --workload $w --impl $impl --no-cpu-baseline --no-c5 --heads --steps 20 --no-stage-timing > gpurun_out/r2_bench_${w}_heads_${impl}.json 2> gpurun_out/r2_bench_${w}_heads_${impl}.err; echo "bench $w heads $impl rc=$?"; grep -v Warning gpurun_out/r2_bench_${w}_heads_${impl}.err | tail -3
   show gpurun_out/r2_bench_${w}_heads_${impl}.json
 done; done
+if [ -n "$NCU" ]; then
 echo "== ncu launches"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 2 --warmup 1 --settle 0 --no-e2e --no-cpu-baseline --no-stage-timing --no-c5 --no-clocks > gpurun_out/ncu_launch_r2.log 2>&1; echo rc=$?; wc -l gpurun_out/launches_r2.csv
 echo "== ncu full (our kernels, one view)"; timeout 900 ncu --set full --clock-control none --import-source on -k "regex:blend|project|emit_tiles|ranges_pack|fill_tail|tile_order" -s 8 -c 8 -o gpurun_out/prof_all_r2 -f python bench.py --steps 2 --warmup 1 --settle 0 --streams 1 --no-e2e --no-cpu-baseline --no-c5 --no-clocks > gpurun_out/ncu_full_r2.log 2>&1; echo rc=$?; tail -2 gpurun_out/ncu_full_r2.log
+fi
