@@ -338,7 +338,8 @@ int mgs_activate_backward(int P, int F,
  *   binning : "point_list" u32[R] (== the reference's point_list), "tile_ids" u32[R] (== high word of the reference's
  *             sorted keys; the low word is the depth bits of point_list[i]), "point_list_unsorted" u32[R],
  *             "tile_ids_unsorted" u32[R], "records" 32-byte records [R]
- *   image   : "final_T" f32[N], "n_contrib" u32[N], "ranges" u32[2T]
+ *   image   : "final_T" f32[N], "n_contrib" u32[N], "ranges" u32[2T], "tile_order" u32[T] (tiles by descending list length,
+ *             ties by tile id: the launch order of the blend CTAs; no reference counterpart)
  * Returns 0, or MGS_ERR_INVALID_ARG for an unknown name.
  */
 int mgs_state_array(const char* which_state, const char* name, char* state, int P_or_R_or_width, int height,

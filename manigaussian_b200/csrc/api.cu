@@ -902,6 +902,7 @@ int mgs_state_array(const char* which_state, const char* name, char* state, int 
 	} else if (w == "image") {
 		ImageState s = ImageState::carve(state, (size_t)a0 * a1, num_tiles(a0, a1));
 		if (n == "final_T") p = s.final_T; else if (n == "n_contrib") p = s.n_contrib; else if (n == "ranges") p = s.ranges;
+		else if (n == "tile_order") p = s.tile_order;
 	}
 	if (!p) return fail(MGS_ERR_INVALID_ARG, "unknown state array " + w + "/" + n);
 	*out_ptr = p;

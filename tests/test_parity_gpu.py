@@ -375,6 +375,21 @@ def test_degenerate_sizes(P, W, H):
     check_stagewise_vs_oracle(inp, 1e-3)
 
 
+@pytest.mark.parametrize("W,H", [(96, 96), (400, 300), (16, 16)])
+def test_tile_launch_order_is_longest_list_first(W, H):
+    """tile_order is a permutation of the tiles, sorted by list length descending, ties by tile id (binning.cu
+    tile_order_kernel); the blend CTAs take their tile through it, so a wrong entry would leave a tile unrendered -- the
+    image parity tests cover that, this one pins the order itself (also for more than 256 tiles... and a single tile)."""
+    inp = util.make_inputs(P=4000, W=W, H=H, F=0, seed=17)
+    ours, _ = util.run_ours(inp, backward=False)
+    lens = (ours["ranges"][:, 1] - ours["ranges"][:, 0]).astype(np.int64)
+    T = lens.size
+    order = ours["tile_order"].astype(np.int64)
+    assert sorted(order.tolist()) == list(range(T))
+    expect = sorted(range(T), key=lambda t: (-lens[t], t))
+    assert order.tolist() == expect
+
+
 def test_opaque_scene_early_termination():
     """Large, nearly opaque splats: most pixels stop at T < 1e-4 long before their tile's list ends (forward `done` path,
     backward walks only the first n_contrib records); n_contrib is compared with the oracle inside the stage-wise check."""

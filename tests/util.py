@@ -199,6 +199,7 @@ def run_ours(inp, backward=True, debug=False, scale_modifier=1.0, prefiltered=Fa
     fw["final_T"] = arr("image", "final_T", imgB, W, H, torch.float32, N)
     fw["n_contrib"] = arr("image", "n_contrib", imgB, W, H, torch.int32, N).astype(np.uint32)
     fw["ranges"] = arr("image", "ranges", imgB, W, H, torch.int32, 2 * T).astype(np.uint32).reshape(T, 2)
+    fw["tile_order"] = arr("image", "tile_order", imgB, W, H, torch.int32, T).astype(np.uint32)
     # expand the 3-bit clamp mask to the reference's bool[P,3] layout
     fw["clamped"] = ((fw["clamped"][:, None] >> np.arange(3)[None, :]) & 1).astype(np.uint8)
     bw = None
