@@ -914,8 +914,10 @@ def main():
     pk0 = _PACKS.get(flat.data_ptr())
 
     streams = None
-    if a.impl == "ours" and a.streams > 1 and V > 1:
-        streams = [torch.cuda.Stream() for _ in range(min(a.streams, V))]
+    if a.impl == "ours" and (a.streams > 1 or V == 1):
+        # truthy = "use the multi-view entry points" (rasterize_views_raw owns the per-view streams; a single view runs on the
+        # caller's stream): no host read-back of the instance count in the timed loop, also for one view
+        streams = [torch.cuda.Stream() for _ in range(min(a.streams, V))] if V > 1 else [torch.cuda.current_stream()]
     cfg["view_streams"] = len(streams) if streams else 1
     meas = {}  # everything MEASURED goes here, `config` only names the workload
     if world > 1 and pk0 is not None:
