@@ -15,7 +15,7 @@ try:
 except Exception as e: print('$1: no json', e)
 PY
 }
-for w in c3 mg; do for impl in ours reference; do
+for w in c3 mg c2; do for impl in ours reference; do
   extra=""; [ "$w" != "c3" ] && extra="--no-c5"
   timeout 900 python bench.py --workload $w --impl $impl --no-cpu-baseline $extra > gpurun_out/r2_bench_${w}_${impl}.json 2> gpurun_out/r2_bench_${w}_${impl}.err; echo "bench $w $impl rc=$?"; grep -v Warning gpurun_out/r2_bench_${w}_${impl}.err | tail -3
   show gpurun_out/r2_bench_${w}_${impl}.json
@@ -26,3 +26,7 @@ if [ -n "$NCU" ]; then
 echo "== ncu launches"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 2 --warmup 1 --settle 0 --no-e2e --no-cpu-baseline --no-stage-timing --no-c5 --no-clocks > gpurun_out/ncu_launch_r2.log 2>&1; echo rc=$?; wc -l gpurun_out/launches_r2.csv
 echo "== ncu full (our kernels, one view)"; timeout 900 ncu --set full --clock-control none --import-source on -k "regex:blend|project|emit_tiles|ranges_pack|fill_tail|tile_order" -s 8 -c 8 -o gpurun_out/prof_all_r2 -f python bench.py --steps 2 --warmup 1 --settle 0 --streams 1 --no-e2e --no-cpu-baseline --no-c5 --no-clocks > gpurun_out/ncu_full_r2.log 2>&1; echo rc=$?; tail -2 gpurun_out/ncu_full_r2.log
 fi
+for impl in ours reference; do
+  timeout 900 python bench.py --workload c4 --impl $impl --no-cpu-baseline --no-c5 > gpurun_out/r2_bench_c4_${impl}.json 2> gpurun_out/r2_bench_c4_${impl}.err; echo "bench c4 $impl rc=$?"; grep -v Warning gpurun_out/r2_bench_c4_${impl}.err | tail -3
+  show gpurun_out/r2_bench_c4_${impl}.json
+done
