@@ -86,3 +86,97 @@ def test_packed_gradient_buffer_layout():
     spans = sorted((v.data_ptr(), v.data_ptr() + v.numel() * 4) for v in pk.views.values())
     assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
     assert sorted(shard_views(8, 0, 4) + shard_views(8, 1, 4) + shard_views(8, 2, 4) + shard_views(8, 3, 4)) == list(range(8))
+
+
+def test_binning_capacity_estimator():
+    """Host logic of the no-sync forward (rasterizer.py): capacities live in geometric buckets, an observed count grows the
+    estimate at once, shrinks it only when the state is more than twice too large, and an overflow is reported and answered
+    with a larger margin.  The counts arrive through pinned status slots guarded by events -- faked here."""
+    import warnings
+    import numpy as np
+    from manigaussian_b200 import rasterizer as R
+
+    prev = 0
+    for n in [1, 4095, 4097, 10_000, 99_999, 1_000_000, 1_441_792, 5_000_000]:
+        c = R._round_capacity(n)
+        assert c >= max(n, 4096) and c - max(n, 4096) <= max(1023, 0.125 * n) and c >= prev
+        assert R._round_capacity(c) == c  # a bucket boundary is a fixed point: stable sizes keep one cached allocation
+        prev = c
+
+    class Ev:
+        def __init__(self, done):
+            self.done = done
+
+        def query(self):
+            return self.done
+
+        def synchronize(self):
+            self.done = True
+
+    saved_cap, saved_pending = dict(R._CAPACITY), list(R._PENDING_STATUS)
+    try:
+        R._CAPACITY.clear()
+        R._PENDING_STATUS[:] = []
+        key = (0, 1000, 64, 64, 0)
+        R._CAPACITY[key] = R._round_capacity(20_000)
+        # an unfinished forward is left alone
+        R._PENDING_STATUS.append((key, np.array([50_000, 0], np.int32), Ev(False), R._CAPACITY[key]))
+        R._poll_status()
+        assert R._CAPACITY[key] == R._round_capacity(20_000) and len(R._PENDING_STATUS) == 1
+        # finished: grows at once to count * 1.25 + 4096
+        R._PENDING_STATUS[0][2].done = True
+        R._poll_status()
+        assert R._CAPACITY[key] == R._round_capacity(50_000 * 1.25 + 4096) and not R._PENDING_STATUS
+        big = R._CAPACITY[key]
+        # a somewhat smaller count keeps the allocation; less than half releases it
+        R._PENDING_STATUS.append((key, np.array([40_000, 0], np.int32), Ev(True), big))
+        R._poll_status()
+        assert R._CAPACITY[key] == big
+        R._PENDING_STATUS.append((key, np.array([10_000, 0], np.int32), Ev(True), big))
+        R._poll_status()
+        assert R._CAPACITY[key] == R._round_capacity(10_000 * 1.25 + 4096) < big // 2
+        # overflow: warned, and the next capacity carries a 1.5x margin
+        cur = R._CAPACITY[key]
+        R._PENDING_STATUS.append((key, np.array([60_000, 1], np.int32), Ev(True), cur))
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            R._poll_status()
+        assert any("tile instances" in str(x.message) for x in w)
+        assert R._CAPACITY[key] == R._round_capacity(60_000 * 1.5 + 4096)
+        # block=True waits for the event instead of skipping it
+        R._PENDING_STATUS.append((key, np.array([200_000, 0], np.int32), Ev(False), R._CAPACITY[key]))
+        R._poll_status(block=True)
+        assert R._CAPACITY[key] == R._round_capacity(200_000 * 1.25 + 4096)
+    finally:
+        R._CAPACITY.clear()
+        R._CAPACITY.update(saved_cap)
+        R._PENDING_STATUS[:] = saved_pending
+
+
+def test_allocator_callback_errors_reach_the_caller():
+    """An exception inside the C library's allocation callback (ctypes would print and swallow it) is stashed on the allocator
+    and re-raised by the call that triggered it; the allocators are released on every error path."""
+    import pytest
+    from manigaussian_b200 import rasterizer as R
+    from manigaussian_b200 import _binding as B
+
+    class Boom(R._Alloc):
+        def alloc(self, nbytes):
+            raise MemoryError("no room for %d bytes" % nbytes)
+
+    a, b = Boom("cpu"), R._Alloc("cpu")
+    assert a.key in R._Alloc._live and b.key in R._Alloc._live
+    assert R._alloc_trampoline(a.key, 1234) == 0 and isinstance(a.error, MemoryError)
+    assert R._alloc_trampoline(b.key, 64) != 0 and b.tensor is not None and b.tensor.numel() >= 64
+    assert R._alloc_trampoline(987654321, 64) == 0  # unknown user handle: NULL, the library reports MGS_ERR_ALLOC
+    with pytest.raises(MemoryError):
+        R._checked((a, b), -3, "unit")
+    assert a.key not in R._Alloc._live and b.key not in R._Alloc._live
+    # a library error code without a stashed exception raises the binding's error and releases too
+    c = R._Alloc("cpu")
+    with pytest.raises(Exception):
+        R._checked((c,), B.lib().mgs_forward_views(0, None, 0, 0, 0, 0, None, None, None, None, None, None, 1.0, None, None, 0, 0, None), "unit")
+    assert c.key not in R._Alloc._live
+    d = R._Alloc("cpu")
+    assert R._checked((d,), 7, "unit") == 7 and d.key in R._Alloc._live
+    d.release()
